@@ -1,0 +1,100 @@
+// Host-side dispatch: PdxConfig -> DevCfg<T> and the (task, physics, noise, rng) template
+// switch.  Included by one translation unit per arithmetic type / physics so that the
+// float64 parity kernels can be compiled with -fmad=false and the build parallelised.
+#pragma once
+#include "pdx_kernels.cuh"
+
+namespace pdx {
+
+enum Kind { KIND_INIT = 0, KIND_RESET = 1, KIND_STEP = 2 };
+
+struct LaunchArgs {
+  const PdxConfig* cfg;
+  const PdxBuffers* buf;
+  const float* actions;
+  const uint8_t* mask;
+  uint64_t seed, counter;
+  double* dump_step;
+  double* dump_reset;
+  double* dump_init;
+  cudaStream_t stream;
+};
+
+template <class T>
+static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
+  const TapeSlots ts = tape_slots_of(p);
+  d.history = p.history; d.agg = p.agg; d.obs_rate = p.obs_rate; d.use_latency = p.use_latency;
+  d.buf_size = p.buf_size; d.use_motor_dynamics = p.use_motor_dynamics;
+  d.reset_distribution = p.reset_distribution; d.ground_effect = p.ground_effect;
+  d.max_episode_steps = p.max_episode_steps; d.core_dim = p.core_dim; d.obs_dim = p.obs_dim;
+  d.dr_on = p.domain_randomization > 0 ? 1 : 0; d.reset_on_nonfinite = p.reset_on_nonfinite; d.auto_reset = p.auto_reset;
+  d.slots_obs_full = ts.obs_full; d.slots_obs_gyro = ts.obs_gyro;
+  d.slots_reset_task = ts.reset_task; d.slots_reset_dr = ts.reset_dr;
+  d.dr = (T)p.domain_randomization; d.time_step = (T)p.time_step; d.mass = (T)p.mass;
+  for (int k = 0; k < 3; ++k) {
+    d.inertia[k] = (T)p.inertia[k]; d.target[k] = (T)p.target_pos[k];
+    d.init_xyz[k] = (T)p.init_xyz[k]; d.drag[k] = (T)p.drag_coeff[k];
+  }
+  d.arm = (T)p.arm;
+  d.gravity = (T)p.gravity; d.thrust2weight = (T)p.thrust2weight; d.max_thrust = (T)p.max_thrust;
+  d.k_mass_dr = (T)p.k_mass_dr; d.ftf1 = (T)p.ftf1; d.hover_x = (T)p.hover_x;
+  d.hover_action = (T)p.hover_action; d.motor_tc = (T)p.motor_time_constant;
+  d.ou_theta = (T)p.ou_theta; d.ou_sigma = (T)p.ou_sigma; d.lpf_ratio = (T)p.lpf_ratio;
+  d.pos_std = (T)p.pos_norm_std; d.pos_unif = (T)p.pos_unif_range; d.vel_std = (T)p.vel_norm_std;
+  d.quat_std = (T)p.quat_norm_std; d.quat_unif = (T)p.quat_unif_range;
+  d.gyro_pi = (T)p.gyro_pi; d.gyro_sigma_b = (T)p.gyro_sigma_b; d.gyro_rw = (T)p.gyro_random_walk;
+  d.gyro_to = (T)p.gyro_turn_on;
+  d.pen_action = (T)p.penalty_action; d.pen_angle = (T)p.penalty_angle; d.pen_spin = (T)p.penalty_spin;
+  d.pen_terminal = (T)p.penalty_terminal; d.pen_velocity = (T)p.penalty_velocity;
+  d.arp = (T)p.action_rate_penalty;
+  for (int k = 0; k < 4; ++k) { d.prop_xy[k][0] = (T)p.prop_xy[k][0]; d.prop_xy[k][1] = (T)p.prop_xy[k][1]; }
+  d.prop_z = (T)p.prop_z; d.gec = (T)p.gnd_eff_coeff; d.prop_r = (T)p.prop_radius;
+  d.ge_hclip = (T)p.gnd_eff_h_clip; d.lin_damp = (T)p.lin_damping; d.ang_damp = (T)p.ang_damping;
+  d.ground_z = (T)p.ground_z;
+}
+
+template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
+  const int64_t n = ka.b.n_envs;
+  const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+  if (kind == KIND_INIT) k_init<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
+  else if (kind == KIND_RESET) k_reset<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
+  else k_step<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
+  return cudaGetLastError();
+}
+
+template <class T, int TASK, int PHYS>
+static cudaError_t launch_nr(int kind, bool noise, int rng, const KArgs<T>& ka, cudaStream_t st) {
+  if (noise) {
+    if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, true, PDX_RNG_PHILOX>(kind, ka, st);
+    return launch_kind<T, TASK, PHYS, true, PDX_RNG_TAPE>(kind, ka, st);
+  }
+  if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, false, PDX_RNG_PHILOX>(kind, ka, st);
+  return launch_kind<T, TASK, PHYS, false, PDX_RNG_TAPE>(kind, ka, st);
+}
+
+// One physics flavour per translation unit.
+template <class T, int PHYS>
+static cudaError_t launch_tu(int kind, const LaunchArgs& la) {
+  KArgs<T> ka;
+  fill_devcfg<T>(*la.cfg, ka.c);
+  ka.b = *la.buf;
+  ka.actions = la.actions; ka.mask = la.mask; ka.seed = la.seed; ka.counter = la.counter;
+  ka.dump_step = la.dump_step; ka.dump_reset = la.dump_reset; ka.dump_init = la.dump_init;
+  const bool noise = la.cfg->observation_noise != 0;
+  // pdx_dump_draws runs the TAPE-mode kernels with dump pointers set.
+  const int rng = (la.dump_step || la.dump_reset || la.dump_init) ? PDX_RNG_TAPE : la.cfg->rng_mode;
+  switch (la.cfg->task) {
+    case PDX_TASK_HOVER: return launch_nr<T, PDX_TASK_HOVER, PHYS>(kind, noise, rng, ka, la.stream);
+    case PDX_TASK_CIRCLE: return launch_nr<T, PDX_TASK_CIRCLE, PHYS>(kind, noise, rng, ka, la.stream);
+    default: return launch_nr<T, PDX_TASK_TAKEOFF, PHYS>(kind, noise, rng, ka, la.stream);
+  }
+}
+
+// Implemented in pdx_tu_*.cu
+cudaError_t launch_f32_simple(int kind, const LaunchArgs& la);
+cudaError_t launch_f32_bullet(int kind, const LaunchArgs& la);
+cudaError_t launch_f64_simple(int kind, const LaunchArgs& la);
+cudaError_t launch_f64_bullet(int kind, const LaunchArgs& la);
+
+}  // namespace pdx

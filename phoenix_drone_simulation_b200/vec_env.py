@@ -1,0 +1,209 @@
+"""Lock-step vectorised Crazyflie environments on one GPU.
+
+`VecEnv` is the new batched API (absent from the reference): N environments advance with
+one fused CUDA kernel launch per `step`, auto-resetting finished episodes inside the same
+launch.  Semantics per environment are the reference's `DroneBaseEnv.reset/step`
+(envs/base.py:382-475 of phoenix_drone_simulation) -- see csrc/pdx_model.cuh.
+
+All tensors are PyTorch CUDA tensors; the kernels are reached through the C ABI of
+libphoenix_b200.so (include/phoenix_b200.h) on torch's current stream.  There is no CPU
+path: constructing a VecEnv without a CUDA device raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .config import EnvConfig
+
+
+class VecEnv:
+    """N environments of one env id, stepped in lock-step on one CUDA device.
+
+    Parameters mirror the reference's `gym.make(env_id, **kwargs)` (config.EnvConfig) plus
+      num_envs, device, dtype (torch.float32 throughput mode / torch.float64 parity mode),
+      seed (Philox key), env_offset (global index of env 0 of this shard: results do not
+      depend on how environments are sharded), rng ('philox' | 'tape'),
+      keep_final_obs (also return the last observation of finished episodes).
+    """
+
+    def __init__(self, env_id, num_envs, device='cuda', dtype=torch.float32, seed=0,
+                 env_offset=0, rng='philox', keep_final_obs=False, **kwargs):
+        if not torch.cuda.is_available():
+            raise _lib.PhoenixB200Error('VecEnv needs a CUDA device: there is no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.PhoenixB200Error('VecEnv needs a CUDA device: there is no CPU fallback')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError('dtype must be torch.float32 or torch.float64')
+        self.dtype = dtype
+        self.num_envs = int(num_envs)
+        self.env_id = env_id
+        self.cfg = kwargs.pop('config', None) or EnvConfig(env_id, **kwargs)
+        self.rng = rng
+        self.pdx = self.cfg.to_pdx(
+            _lib.PDX_DTYPE_F32 if dtype == torch.float32 else _lib.PDX_DTYPE_F64,
+            _lib.PDX_RNG_PHILOX if rng == 'philox' else _lib.PDX_RNG_TAPE)
+        self.obs_dim = int(self.pdx.obs_dim)
+        self.core_dim = int(self.pdx.core_dim)
+        self.act_dim = 4
+        self.max_episode_steps = int(self.pdx.max_episode_steps)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.env_offset = int(env_offset)
+        self._counter = 0
+        n, dev = self.num_envs, self.device
+        self.n_quads = self.lib.pdx_state_quads(C.byref(self.pdx))
+        self.state = torch.zeros((self.n_quads, n, 4), dtype=dtype, device=dev)
+        self.obs = torch.zeros((n, self.obs_dim), dtype=dtype, device=dev)
+        self.reward = torch.zeros(n, dtype=dtype, device=dev)
+        self.cost = torch.zeros(n, dtype=dtype, device=dev)
+        self._terminated = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._truncated = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terminated = self._terminated.view(torch.bool)
+        self.truncated = self._truncated.view(torch.bool)
+        self.episode_return = torch.zeros(n, dtype=dtype, device=dev)
+        self.episode_length = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.final_obs = torch.zeros((n, self.obs_dim), dtype=dtype, device=dev) if keep_final_obs else None
+        self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.clear_episode_stats()
+        rs, ss, is_ = C.c_int(), C.c_int(), C.c_int()
+        self.lib.pdx_tape_slots(C.byref(self.pdx), C.byref(rs), C.byref(ss), C.byref(is_))
+        self.tape_slots = dict(reset=rs.value, step=ss.value, init=is_.value)
+        self._tapes = dict(step=None, reset=None, init=None)
+        self.step_bytes = int(self.lib.pdx_step_bytes(C.byref(self.pdx)))
+        self._buf = _lib.PdxBuffers()
+        self._fill_buffers()
+        if rng == 'philox':
+            self._construct()
+
+    # ----------------------------------------------------------------------------------------
+    def _fill_buffers(self):
+        b = self._buf
+        b.n_envs, b.env_offset, b.device = self.num_envs, self.env_offset, self.device.index
+        b.state, b.obs = self.state.data_ptr(), self.obs.data_ptr()
+        b.reward, b.cost = self.reward.data_ptr(), self.cost.data_ptr()
+        b.terminated, b.truncated = self._terminated.data_ptr(), self._truncated.data_ptr()
+        b.final_obs = self.final_obs.data_ptr() if self.final_obs is not None else None
+        b.episode_return = self.episode_return.data_ptr()
+        b.episode_length = self.episode_length.data_ptr()
+        b.episode_stats = self.stats.data_ptr()
+        for k in ('step', 'reset', 'init'):
+            t = self._tapes[k]
+            setattr(b, 'tape_' + k, t.data_ptr() if t is not None else None)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _next_counter(self):
+        self._counter += 1
+        return self._counter
+
+    def _construct(self):
+        """Constructor semantics of the reference (state zeroed, nominal parameters, the one
+        compute_observation() call of base.py:143)."""
+        _lib.check(self.lib.pdx_init(C.byref(self.pdx), C.byref(self._buf), self.seed, 0, self._stream()))
+
+    # ---- tape mode (parity harness) ---------------------------------------------------------
+    def set_tapes(self, step=None, reset=None, init=None):
+        """Standardised draws, float64 CUDA tensors of shape [slots, num_envs]."""
+        for k, t in (('step', step), ('reset', reset), ('init', init)):
+            if t is not None:
+                assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+                assert t.shape == (self.tape_slots[k], self.num_envs), (k, tuple(t.shape), self.tape_slots[k])
+                self._tapes[k] = t
+        self._fill_buffers()
+
+    def construct_from_tape(self, init=None):
+        if init is not None:
+            self.set_tapes(init=init)
+        self._construct()
+
+    # ---- API ------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        """Reset all environments (or those where `mask` is True); returns obs [N, D]."""
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = C.c_void_p(mask.data_ptr())
+        _lib.check(self.lib.pdx_reset(C.byref(self.pdx), C.byref(self._buf), mptr, self.seed,
+                                      self._next_counter(), self._stream()))
+        return self.obs
+
+    def step(self, actions):
+        """actions: float32 CUDA tensor [N, 4].  Returns (obs, reward, terminated, truncated,
+        info); the tensors are owned by the VecEnv and overwritten by the next call."""
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert actions.shape == (self.num_envs, 4)
+        _lib.check(self.lib.pdx_step(C.byref(self.pdx), C.byref(self._buf), C.c_void_p(actions.data_ptr()),
+                                     self.seed, self._next_counter(), self._stream()))
+        info = {'cost': self.cost, 'episode_return': self.episode_return,
+                'episode_length': self.episode_length}
+        if self.final_obs is not None:
+            info['final_observation'] = self.final_obs
+        return self.obs, self.reward, self.terminated, self.truncated, info
+
+    # ---- validation: production Philox draws copied out in tape layout ------------------------
+    def dump_init(self):
+        t = torch.zeros((max(self.tape_slots['init'], 1), self.num_envs), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pdx_dump_draws(C.byref(self.pdx), C.byref(self._buf), None, self.seed, 0,
+                                           None, None, C.c_void_p(t.data_ptr()), self._stream()))
+        return t[:self.tape_slots['init']]
+
+    def dump_reset(self):
+        t = torch.zeros((max(self.tape_slots['reset'], 1), self.num_envs), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pdx_dump_draws(C.byref(self.pdx), C.byref(self._buf), None, self.seed,
+                                           self._next_counter(), None, C.c_void_p(t.data_ptr()), None,
+                                           self._stream()))
+        return self.obs, t[:self.tape_slots['reset']]
+
+    def dump_step(self, actions):
+        ts = torch.zeros((max(self.tape_slots['step'], 1), self.num_envs), dtype=torch.float64, device=self.device)
+        tr = torch.zeros((max(self.tape_slots['reset'], 1), self.num_envs), dtype=torch.float64, device=self.device)
+        actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        _lib.check(self.lib.pdx_dump_draws(C.byref(self.pdx), C.byref(self._buf), C.c_void_p(actions.data_ptr()),
+                                           self.seed, self._next_counter(), C.c_void_p(ts.data_ptr()),
+                                           C.c_void_p(tr.data_ptr()), None, self._stream()))
+        return ts[:self.tape_slots['step']], tr[:self.tape_slots['reset']]
+
+    # ---- episode statistics (block-reduced in the step kernel) ------------------------------
+    def clear_episode_stats(self):
+        self.stats.copy_(torch.tensor([0., 0., 0., 0., 1e300, -1e300, 1e300, -1e300], dtype=torch.float64))
+
+    def episode_stats(self, clear=False):
+        """[n, sum ret, sum ret^2, sum len, min ret, max ret, min len, max len] (float64)."""
+        s = self.stats.clone()
+        if clear:
+            self.clear_episode_stats()
+        return s
+
+    # ---- state access (checkpointing, parity harness) ------------------------------------------
+    def _field(self, name):
+        fw, nw = C.c_int(), C.c_int()
+        _lib.check(self.lib.pdx_state_field(C.byref(self.pdx), name.encode(), C.byref(fw), C.byref(nw)))
+        return fw.value, nw.value
+
+    def get_state(self, name):
+        fw, nw = self._field(name)
+        return torch.stack([self.state[w // 4, :, w % 4] for w in range(fw, fw + nw)], dim=1)
+
+    def set_state(self, name, value):
+        fw, nw = self._field(name)
+        value = torch.as_tensor(value, dtype=self.dtype, device=self.device).reshape(-1, nw)
+        value = value.expand(self.num_envs, nw)
+        for k, w in enumerate(range(fw, fw + nw)):
+            self.state[w // 4, :, w % 4] = value[:, k]
+
+    def state_dict(self):
+        return {'state': self.state.clone(), 'counter': self._counter, 'seed': self.seed,
+                'env_id': self.env_id, 'stats': self.stats.clone()}
+
+    def load_state_dict(self, sd):
+        assert sd['env_id'] == self.env_id and sd['state'].shape == self.state.shape
+        self.state.copy_(sd['state'])
+        self.stats.copy_(sd['stats'])
+        self._counter = int(sd['counter'])
+        self.seed = int(sd['seed'])

@@ -1,0 +1,128 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+that include/phoenix_b200.h declares, its structs match the ctypes mirror, the query
+functions agree with the golden fixtures, and -- with no CUDA device -- every compute entry
+point FAILS LOUDLY (there is no CPU fallback on the product path)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import phoenix_drone_simulation_b200 as pds
+from phoenix_drone_simulation_b200 import lib as L
+from golden_util import golden_names, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    if not os.path.exists(L.LIB_PATH):
+        from phoenix_drone_simulation_b200.build import build
+        build()
+    return L.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, 'include', 'phoenix_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(pdx_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(L.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_sizes_and_version(lib):
+    assert lib.pdx_abi_version() == L.ABI_VERSION
+    assert lib.pdx_config_size() == C.sizeof(L.PdxConfig)
+    assert lib.pdx_buffers_size() == C.sizeof(L.PdxBuffers)
+
+
+@pytest.mark.parametrize('env_id,obs_dim', [
+    ('DroneHoverSimpleEnv-v0', 34), ('DroneHoverBulletEnv-v0', 34), ('DroneCircleSimpleEnv-v0', 40),
+    ('DroneCircleBulletEnv-v0', 40), ('DroneTakeOffSimpleEnv-v0', 48), ('DroneTakeOffBulletEnv-v0', 48)])
+def test_observation_widths(lib, env_id, obs_dim):
+    """D = H (C + 4): 34 / 40 / 48 at H = 2 (verified by running the reference)."""
+    c = pds.EnvConfig(env_id).to_pdx()
+    assert c.obs_dim == obs_dim
+    c = pds.EnvConfig(env_id, observation_history_size=8).to_pdx()
+    assert c.obs_dim == 4 * obs_dim
+
+
+def test_noise_off_hover_width(lib):
+    assert pds.EnvConfig('DroneHoverSimpleEnv-v0', observation_noise=0).to_pdx().obs_dim == 42
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_tape_slots_match_reference_draw_counts(lib, name):
+    """The per-phase draw counts of the engine equal what the unmodified reference consumed."""
+    g = load_golden(name)
+    kw = dict(g['kwargs'])
+    c = pds.EnvConfig(g['env_id'], **kw).to_pdx()
+    rs, ss, is_ = C.c_int(), C.c_int(), C.c_int()
+    assert lib.pdx_tape_slots(C.byref(c), C.byref(rs), C.byref(ss), C.byref(is_)) == 0
+    assert ss.value == g['step_tape'].shape[1]
+    assert rs.value == g['reset_tape'].shape[1]
+    assert is_.value == g['init_tape'].shape[0]
+    assert c.obs_dim == g['obs'].shape[1]
+
+
+def test_state_layout(lib):
+    c = pds.EnvConfig('DroneHoverSimpleEnv-v0').to_pdx()
+    fw, nw = C.c_int(), C.c_int()
+    seen = set()
+    for name in ('xyz', 'vel', 'rpy', 'omega', 'ou', 'last_action', 'ep_return', 'ep_length',
+                 'hist_phase', 'gyro_bias', 'gyro_lpf', 'dt', 'mass', 'inertia', 'ftf1'):
+        assert lib.pdx_state_field(C.byref(c), name.encode(), C.byref(fw), C.byref(nw)) == 0
+        words = set(range(fw.value, fw.value + nw.value))
+        assert not (words & seen), name
+        seen |= words
+    assert len(seen) == 35                      # 29 per-step words + 6 per-episode constants
+    assert lib.pdx_state_field(C.byref(c), b'hist', C.byref(fw), C.byref(nw)) == 0
+    assert fw.value == 36 and nw.value == 20    # one history slot: 13 + 4 words in 5 quads
+    assert lib.pdx_state_quads(C.byref(c)) == 14
+    assert lib.pdx_state_field(C.byref(c), b'quat', C.byref(fw), C.byref(nw)) != 0     # Bullet only
+    assert b'does not exist' in lib.pdx_last_error()
+    # algorithmic bytes per env-step: 52 words read, 46 written, obs 34, r, cost
+    assert lib.pdx_step_bytes(C.byref(c)) == (52 + 46 + 34 + 2) * 4 + 16 + 2
+
+
+def test_unsupported_configurations_are_rejected(lib):
+    with pytest.raises(NotImplementedError):
+        pds.EnvConfig('DroneHoverSimpleEnv-v0', control_mode='Attitude')
+    with pytest.raises(KeyError):
+        pds.EnvConfig('DroneFooEnv-v0')
+    with pytest.raises(L.PhoenixB200Error):
+        pds.EnvConfig('DroneHoverBulletEnv-v0', aggregate_phy_steps=1).to_pdx()   # agg % obs_rate
+    with pytest.raises(L.PhoenixB200Error):
+        pds.EnvConfig('DroneHoverSimpleEnv-v0', observation_history_size=0).to_pdx()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour WITHOUT a GPU')
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product path must raise, not silently compute on the CPU."""
+    with pytest.raises(L.PhoenixB200Error):
+        pds.VecEnv('DroneHoverSimpleEnv-v0', 4)
+    with pytest.raises(L.PhoenixB200Error):
+        pds.make('DroneHoverSimpleEnv-v0')
+    c = pds.EnvConfig('DroneHoverSimpleEnv-v0').to_pdx()
+    host = np.zeros(4096, dtype=np.float32)
+    b = L.PdxBuffers()
+    b.n_envs = 4
+    for f in ('state', 'obs', 'reward', 'cost', 'terminated', 'truncated'):
+        setattr(b, f, host.ctypes.data)
+    assert lib.pdx_step(C.byref(c), C.byref(b), host.ctypes.data, 0, 1, None) == -3     # PDX_ERR_NO_DEVICE
+    assert b'no CPU path' in lib.pdx_last_error()
+    assert lib.pdx_gae(4, 4, *([host.ctypes.data] * 5), 0.99, 0.95, 1.0, 0, *([host.ctypes.data] * 3), None) == -3
+
+
+def test_product_package_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, 'phoenix_drone_simulation_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f

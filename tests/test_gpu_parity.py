@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA engine (through the C ABI / VecEnv) against
+
+  1. the golden vectors recorded from the UNMODIFIED reference (tests/golden), by replaying
+     the recorded random draws in the kernels' tape mode -- float64: tolerance 1e-9
+     (observed ~1e-13), flags/reset indices exact; float32: tolerance stated per test;
+  2. the oracle on the draws the production Philox path really consumed (pdx_dump_draws);
+  3. size-independent properties at BASELINE.json's full size (65,536 envs).
+
+Everything here needs a CUDA device (`-m gpu`) and nothing reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-9
+
+
+def _vec(*a, **k):
+    from phoenix_drone_simulation_b200 import VecEnv
+    return VecEnv(*a, **k)
+
+
+def replay_golden_on_gpu(g, dtype, n_copies=3):
+    """Drive a tape-mode VecEnv with the golden's actions and recorded draws (every env column
+    gets the same tape).  Mirrors golden_util.replay_oracle's protocol via in-kernel auto-reset."""
+    dev = torch.device('cuda')
+    T = g['actions'].shape[0]
+    env = _vec(g['env_id'], n_copies, dtype=dtype, rng='tape', keep_final_obs=True, **g['kwargs'])
+    S, R = env.tape_slots['step'], env.tape_slots['reset']
+
+    def col(v, slots):
+        t = torch.zeros((max(slots, 1), n_copies), dtype=torch.float64, device=dev)
+        if slots:
+            t[:slots] = torch.as_tensor(v[:slots], dtype=torch.float64, device=dev)[:, None]
+        return t[:slots] if slots else t[:0]
+
+    env.construct_from_tape(col(g['init_tape'], env.tape_slots['init']))
+    env.set_tapes(reset=col(g['reset_tape'][0], R))
+    out = dict(obs=[], rew=[], terminated=[], truncated=[], cost=[], state=[], reset_obs=[], reset_after=[],
+               reset_state=[])
+
+    def snap():
+        if 'Simple' in g['env_id']:
+            return torch.cat([env.get_state(k) for k in ('xyz', 'rpy', 'vel', 'omega')], dim=1).double().cpu().numpy()
+        return torch.cat([env.get_state(k) for k in ('xyz', 'vel')], dim=1).double().cpu().numpy()
+
+    o = env.reset()
+    out['reset_obs'].append(o.double().cpu().numpy().copy())
+    out['reset_after'].append(-1)
+    out['reset_state'].append(snap())
+    reset_of_step = {int(t): e for e, t in enumerate(g['reset_after'])}
+    acts = torch.as_tensor(g['actions'], device=dev)
+    for t in range(T):
+        e = reset_of_step.get(t)
+        env.set_tapes(step=col(g['step_tape'][t], S),
+                      reset=col(g['reset_tape'][e] if e is not None else np.zeros(R), R))
+        obs, rew, term, trunc, info = env.step(acts[t].expand(n_copies, 4).contiguous())
+        fin = (term | trunc).cpu().numpy()
+        out['terminated'].append(term.cpu().numpy().copy())
+        out['truncated'].append(trunc.cpu().numpy().copy())
+        out['rew'].append(rew.double().cpu().numpy().copy())
+        out['cost'].append(info['cost'].double().cpu().numpy().copy())
+        if fin.any():
+            out['obs'].append(info['final_observation'].double().cpu().numpy().copy())
+            out['reset_obs'].append(obs.double().cpu().numpy().copy())
+            out['reset_after'].append(t)
+            out['reset_state'].append(snap())
+            out['state'].append(None)
+        else:
+            out['obs'].append(obs.double().cpu().numpy().copy())
+            out['state'].append(snap())
+    return out
+
+
+def compare_with_golden(g, out, tol, upto=None):
+    """Returns the max abs error over (obs, reward, state, reset obs); asserts flags exactly."""
+    T = g['actions'].shape[0] if upto is None else upto
+    err = 0.0
+    simple = 'Simple' in g['env_id']
+    for t in range(T):
+        for c in range(out['terminated'][t].shape[0]):
+            assert bool(out['terminated'][t][c]) == bool(g['terminated'][t]), ('terminated', t)
+            assert out['cost'][t][c] == g['cost'][t], ('cost', t)
+        fin_ref = np.isfinite(g['obs'][t])
+        for c in range(out['obs'][t].shape[0]):
+            err = max(err, float(np.max(np.abs(out['obs'][t][c][fin_ref] - g['obs'][t][fin_ref]))))
+            if np.isfinite(g['rew'][t]):
+                err = max(err, abs(out['rew'][t][c] - g['rew'][t]))
+            if out['state'][t] is not None:
+                ref = g['state'][t] if simple else g['state'][t][[0, 1, 2, 6, 7, 8]]
+                m = np.isfinite(ref)
+                err = max(err, float(np.max(np.abs(out['state'][t][c][m] - ref[m]))))
+    n_res = sum(1 for r in out['reset_after'] if r < T)
+    assert [int(r) for r in out['reset_after'][:n_res]] == [int(r) for r in g['reset_after'] if r < T]
+    for e in range(n_res):
+        # quaternion sign: q and -q are the same rotation (Bullet round trip), compare both
+        a, b = out['reset_obs'][e], g['reset_obs'][e]
+        err = max(err, float(np.max(np.abs(a - b[None, :]))))
+    assert err <= tol, err
+    return err
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_float64_matches_reference_goldens(name):
+    """float64 kernels on the reference's own recorded draws: <= 1e-9 on every observation,
+    reward and state word of every step; terminated / cost flags and reset indices exact."""
+    g = load_golden(name)
+    out = replay_golden_on_gpu(g, torch.float64)
+    err = compare_with_golden(g, out, F64_TOL)
+    print(f'{name}: float64 max abs err vs reference = {err:.3e}')
+
+
+F32_CASES = ['config1_hover_simple_default', 'config1_hover_simple_det', 'circle_simple_default',
+             'takeoff_simple_det', 'hover_bullet_default', 'hover_simple_nearhover_det']
+
+
+@pytest.mark.parametrize('name', F32_CASES)
+def test_float32_tracks_reference_goldens(name):
+    """float32 kernels vs the float64 reference on the same draws.  Episodes restart from
+    recorded draws, so round-off does not accumulate across episodes; tolerance 2e-3 abs on
+    obs/reward/state (attitude error feeds horizontal acceleration, error grows ~t^2; the
+    500-step near-hover golden is the worst case).  Flags must agree up to the first step
+    where the reference sits within float32 resolution of a threshold."""
+    g = load_golden(name)
+    out = replay_golden_on_gpu(g, torch.float32, n_copies=2)
+    T = g['actions'].shape[0]
+    first_bad = T
+    for t in range(T):
+        if bool(out['terminated'][t][0]) != bool(g['terminated'][t]) or out['cost'][t][0] != g['cost'][t]:
+            first_bad = t
+            break
+    err = compare_with_golden(g, out, 2e-3, upto=first_bad)
+    print(f'{name}: float32 max abs err = {err:.3e}, flags identical for {first_bad}/{T} steps')
+    assert first_bad >= min(T, 100), 'float32 flags diverged early'
+
+
+def test_philox_path_equals_tape_semantics():
+    """The production Philox path and the parity (tape) path are the same arithmetic: dump the
+    draws the Philox kernels consume, replay them through the CPU oracle, compare (float64)."""
+    from oracle.phoenix_oracle import OracleEnv, TapeSource
+    for env_id in ('DroneHoverSimpleEnv-v0', 'DroneCircleBulletEnv-v0', 'DroneTakeOffSimpleEnv-v0'):
+        N, T = 16, 40
+        env = _vec(env_id, N, dtype=torch.float64, seed=1234, keep_final_obs=True)
+        twin = _vec(env_id, N, dtype=torch.float64, seed=1234, keep_final_obs=True)
+        init_tape = env.dump_init().cpu().numpy()
+        obs0, rt = env.dump_reset()
+        obs0 = obs0.cpu().numpy().copy()
+        assert torch.equal(twin.reset(), env.obs)
+        reset_tapes = [[rt.cpu().numpy()[:, c].copy()] for c in range(N)]
+        step_tapes = [[] for _ in range(N)]
+        rng = np.random.default_rng(5)
+        hover = env.cfg.hover_action
+        acts = (hover + 0.3 * rng.standard_normal((T, N, 4))).astype(np.float32)
+        rec = []
+        for t in range(T):
+            a = torch.as_tensor(acts[t], device='cuda')
+            ts, tr = env.dump_step(a)
+            o2, r2, te2, tr2, _ = twin.step(a)
+            # production kernel == dump kernel (same arithmetic, different instantiation)
+            assert torch.allclose(o2, env.obs, rtol=0, atol=1e-12) and torch.equal(te2, env.terminated)
+            fin = (env.terminated | env.truncated).cpu().numpy()
+            rec.append((env.obs.cpu().numpy().copy(), env.reward.cpu().numpy().copy(),
+                        env.terminated.cpu().numpy().copy(), env.final_obs.cpu().numpy().copy(), fin))
+            ts, tr = ts.cpu().numpy(), tr.cpu().numpy()
+            for c in range(N):
+                step_tapes[c].append(ts[:, c].copy())
+                if fin[c]:
+                    reset_tapes[c].append(tr[:, c].copy())
+        worst = 0.0
+        for c in range(0, N, 3):
+            o = OracleEnv(env_id, TapeSource(reset_tapes[c], step_tapes[c], init_tape[:, c]))
+            ob, _ = o.reset()
+            worst = max(worst, np.max(np.abs(ob - obs0[c])))
+            n_ep = 0
+            for t in range(T):
+                ob, r, term, _, info = o.step(acts[t, c])
+                n_ep += 1
+                obs_g, rew_g, term_g, fin_obs_g, fin = rec[t]
+                assert bool(term_g[c]) == bool(term)
+                got = fin_obs_g[c] if fin[c] else obs_g[c]
+                worst = max(worst, np.max(np.abs(got - ob)), abs(rew_g[c] - r))
+                if term or n_ep == 500:
+                    ob, _ = o.reset()
+                    n_ep = 0
+                    worst = max(worst, np.max(np.abs(obs_g[c] - ob)))
+        print(f'{env_id}: Philox path vs oracle on dumped draws: max abs err {worst:.3e}')
+        assert worst < 1e-9
+
+
+def test_cuda_philox_is_bit_exact():
+    """Raw generator check through the dump: float64 uniforms are x * 2^-32 exactly."""
+    from oracle.philox import engine_raw, SITE_RESET
+    env = _vec('DroneHoverSimpleEnv-v0', 8, dtype=torch.float64, seed=0x1234567890abcdef, env_offset=5)
+    _, rt = env.dump_reset()
+    rt = rt.cpu().numpy()
+    for c in range(8):
+        for call in range(3):
+            raw = engine_raw(0x1234567890abcdef, 5 + c, env._counter, SITE_RESET + call)
+            got = (rt[4 * call:4 * call + 4, c] * 4294967296.0).astype(np.uint64)
+            assert [int(x) for x in got] == [int(x) for x in raw]
+
+
+def test_sharding_invariance_and_determinism():
+    """Results depend on (seed, global env index, step), not on the shard layout."""
+    N, T = 256, 30
+    full = _vec('DroneHoverSimpleEnv-v0', N, seed=7)
+    lo = _vec('DroneHoverSimpleEnv-v0', N // 2, seed=7, env_offset=0)
+    hi = _vec('DroneHoverSimpleEnv-v0', N // 2, seed=7, env_offset=N // 2)
+    again = _vec('DroneHoverSimpleEnv-v0', N, seed=7)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    o = full.reset().clone()
+    assert torch.equal(o, torch.cat([lo.reset(), hi.reset()]))
+    assert torch.equal(o, again.reset())
+    for _ in range(T):
+        a = torch.rand((N, 4), device='cuda', generator=g) * 2 - 1
+        o, r, te, tr, _ = full.step(a)
+        o1, r1, te1, _, _ = lo.step(a[:N // 2].contiguous())
+        o2, r2, te2, _, _ = hi.step(a[N // 2:].contiguous())
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2]))
+        assert torch.equal(te, torch.cat([te1, te2]))
+        o3, r3, _, _, _ = again.step(a)
+        assert torch.equal(o, o3) and torch.equal(r, r3)
+
+
+@pytest.mark.parametrize('env_id', ['DroneHoverSimpleEnv-v0', 'DroneCircleSimpleEnv-v0',
+                                    'DroneTakeOffSimpleEnv-v0', 'DroneHoverBulletEnv-v0'])
+def test_full_size_properties(env_id):
+    """65,536 lock-step envs (BASELINE config 2 size), float32, Philox: properties that hold for
+    every trajectory of the reference -- history consistency, reward bound, terminal penalty,
+    time-limit bookkeeping and the block-reduced episode statistics (checksum of checksums)."""
+    N, T = 65536, 60
+    env = _vec(env_id, N, seed=3, reset_on_nonfinite=env_id.startswith('DroneTakeOff'))
+    C4 = env.core_dim + 4
+    g = torch.Generator(device='cuda').manual_seed(1)
+    prev = env.reset().clone()
+    assert torch.isfinite(prev).all()
+    n_done = 0
+    sum_ret = torch.zeros((), dtype=torch.float64, device='cuda')
+    sum_len = 0
+    for t in range(T):
+        a = env.cfg.hover_action + 0.4 * torch.randn((N, 4), device='cuda', generator=g)
+        obs, rew, term, trunc, info = env.step(a)
+        fin = term | trunc
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert (rew <= 0).all()                                   # r = -dist - penalties
+        if 'Hover' in env_id or 'Circle' in env_id:
+            assert (rew[term] <= -100).all()                      # terminal penalty
+            assert (rew[~term] > -100).all()
+        keep = ~fin
+        # sliding window: entry 0 of obs(k) is entry 1 of obs(k-1) (H = 2), except the action
+        # slots of the first two steps of a Bullet episode (aliasing quirk)
+        a_ok = obs[keep][:, :env.core_dim], prev[keep][:, C4:C4 + env.core_dim]
+        assert torch.equal(*a_ok)
+        assert (info['episode_length'][fin] >= 1).all() and (info['episode_length'][~fin] == 0).all()
+        n_done += int(fin.sum())
+        sum_ret += info['episode_return'][fin].double().sum()
+        sum_len += int(info['episode_length'][fin].sum())
+        prev = obs.clone()
+    s = env.episode_stats().cpu().numpy()
+    assert int(s[0]) == n_done and int(s[3]) == sum_len
+    assert abs(s[1] - float(sum_ret)) <= 1e-6 * max(1.0, abs(float(sum_ret)))
+    if n_done:
+        assert s[4] <= s[1] / s[0] <= s[5] and 1 <= s[6] <= s[7] <= 500
+    print(f'{env_id}: {n_done} episodes finished in {T} steps of {N} envs')
+
+
+def test_time_limit_truncation():
+    env = _vec('DroneTakeOffSimpleEnv-v0', 64, seed=0, max_episode_steps=20, observation_noise=0,
+               domain_randomization=-1)
+    env.reset()
+    a = torch.full((64, 4), -1.0, device='cuda')
+    for t in range(1, 45):
+        _, _, term, trunc, info = env.step(a)
+        assert not term.any()
+        assert bool(trunc.all()) == (t % 20 == 0)
+        if t % 20 == 0:
+            assert (info['episode_length'] == 20).all()
+
+
+def test_domain_randomisation_and_reset_distributions():
+    """Statistical check of the Philox-driven reset (A.5): ranges and means of the sampled
+    parameters at 65,536 envs."""
+    env = _vec('DroneHoverBulletEnv-v0', 65536, seed=11)
+    env.reset()
+    c = env.pdx
+    for name, nominal in (('dt', c.time_step), ('mass', c.mass), ('ftf1', c.ftf1)):
+        v = env.get_state(name)[:, 0].double()
+        assert v.min() >= nominal * 0.9 * (1 - 1e-6) and v.max() <= nominal * 1.1 * (1 + 1e-6)
+        assert abs(float(v.mean()) / nominal - 1) < 2e-3
+        assert abs(float(v.std()) / nominal - 0.2 / 12 ** 0.5) < 2e-3
+    xyz = env.get_state('xyz').double()
+    assert (xyz[:, :2].abs() <= 0.25 + 1e-6).all() and ((xyz[:, 2] - 1).abs() <= 0.25 + 1e-6).all()
+    x = env.get_state('motor_x').double()
+    assert abs(float(x.mean()) - c.hover_x) < 1e-3 and abs(float(x.std()) - 0.02) < 5e-4
+    k = env.get_state('motor_k').double()
+    assert abs(float(k.mean()) - 0.028 * 9.81 * 1.8 / 4) < 1e-4
+
+
+def test_normal_draws_are_standard():
+    env = _vec('DroneHoverSimpleEnv-v0', 65536, seed=5)
+    env.dump_init()
+    env.dump_reset()
+    ts, _ = env.dump_step(torch.zeros((65536, 4), device='cuda'))
+    z = torch.cat([ts[0:4], ts[16:25], ts[37:40], ts[43:46], ts[49:58], ts[58:61]]).flatten()   # normal slots
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3
+    assert abs(float((z ** 4).mean()) - 3) < 0.05
+    u = torch.cat([ts[40:43], ts[61:64]]).flatten()                                           # uniform slots
+    assert 0 <= float(u.min()) and float(u.max()) < 1 and abs(float(u.mean()) - 0.5) < 3e-3
+
+
+def test_single_env_dropin_api():
+    """tests/test_envs.py of the reference: make, reset, run one episode, check types."""
+    import phoenix_drone_simulation_b200 as pds
+    for env_id in pds.ENV_IDS:
+        env = pds.make(env_id, seed=1)
+        x, info = env.reset(seed=42)
+        assert isinstance(x, np.ndarray) and x.shape == env.observation_space.shape and info == {}
+        assert env.action_space.shape == (4,)
+        done, steps = False, 0
+        while not done:
+            x, r, terminated, truncated, info = env.step(env.action_space.sample())
+            assert isinstance(r, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+            assert isinstance(info, dict) and 'cost' in info and x.shape == env.observation_space.shape
+            steps += 1
+            done = terminated or truncated
+        assert 1 <= steps <= 500
+        assert env._max_episode_steps == 500
+        env.close()
