@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched Crazyflie stepping engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
+    python bench.py --impl reference [--gpus N] --steps K ...    # CPU arm (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        # one rank per GPU
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "Config 2"): DroneHoverSimpleEnv-v0,
+65,536 lock-step environments per GPU, 10 % domain randomisation, observation noise on,
+history H = 2, float32 SoA state, on-device Philox, U(-1,1) float32 actions, auto-reset.
+
+One bench "step" = one rollout segment of `--inner` (default 64) env.steps of every
+environment, written into [inner, N, .] rollout tensors.  Actions and observations stream
+through ring buffers larger than L2; the 65,536-env state itself (~13 MB) is L2-resident by the
+workload's definition -- `config.l2` says so, and `roofline_hbm_resident_off` repeats the
+measurement at 4 Mi environments per GPU where the state (0.9 GB) cannot stay in L2.
+
+JSON keys follow the driver contract: value (device-resident inputs, CUDA events, max over
+ranks), e2e (host buffers, H2D/D2H inside the timed region), roofline, cpu_baseline, clocks,
+gpu_launches.  Only the `cpu_baseline` leg and `--impl reference` execute oracle/.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_ID = 'DroneHoverSimpleEnv-v0'
+METRIC = 'env-steps/sec'
+UNIT = 'env-steps/s'
+L2_BYTES = 126 * 1024 * 1024
+HBM_FALLBACK_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# =============================================================================================
+#  CPU arm: the oracle port (numpy restatement of the reference env), one env per process --
+#  the reference's own parallel model is one env per MPI rank (algs/iwpg/iwpg.py:90).
+# =============================================================================================
+def _cpu_worker(args):
+    env_id, seed, budget_s, max_steps = args
+    import numpy as np
+    from oracle.phoenix_oracle import OracleEnv, NumpyGlobalSource
+    np.random.seed(seed)
+    env = OracleEnv(env_id, NumpyGlobalSource())
+    rng = np.random.default_rng(seed)
+    env.reset()
+    acts = rng.uniform(-1, 1, (4096, 4)).astype(np.float32)
+    n, ep_len = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        _, _, terminated, _, _ = env.step(acts[n & 4095])
+        n += 1
+        ep_len += 1
+        if terminated or ep_len == 500:
+            env.reset()
+            ep_len = 0
+        if (n & 63) == 0 and time.perf_counter() - t0 >= budget_s:
+            break
+        if max_steps and n >= max_steps:
+            break
+    return n, time.perf_counter() - t0
+
+
+def cpu_env_steps_per_sec(env_id, budget_s, procs=None, max_steps=0):
+    """Σ steps / wall over `procs` worker processes (default: all host cores)."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(env_id, 1000 + 10000 * r, budget_s, max_steps) for r in range(procs)])
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return steps / busy, procs, steps, wall
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    K, W = a.steps, a.warmup
+    per_step_budget = min(2.0, 120.0 / max(1, K + W))          # whole run ends within minutes
+    procs = os.cpu_count() or 1
+    for _ in range(W):
+        cpu_env_steps_per_sec(a.env_id, per_step_budget / 4, procs)
+    tot_steps, tot_time = 0, 0.0
+    for _ in range(K):
+        v, _, steps, _ = cpu_env_steps_per_sec(a.env_id, per_step_budget, procs)
+        tot_steps += steps
+        tot_time += steps / v
+    value = tot_steps / tot_time
+    sample = (f'{K} samples of {per_step_budget:.2f} s on {procs} processes, one oracle env per process, '
+              f'U(-1,1) float32 actions, auto-reset ({tot_steps} env-steps in total)')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': K,
+        'warmup': W, 'ms_per_step': 1e3 * tot_time / K, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(a, a.num_envs),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================================
+#  clocks during the timed region (NVML; same fields as the recipe's nvidia-smi line)
+# =============================================================================================
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.thread = None
+
+    def _reasons(self, mask):
+        nv = self.nv
+        names = {'hw_slowdown': 'nvmlClocksThrottleReasonHwSlowdown',
+                 'hw_thermal_slowdown': 'nvmlClocksThrottleReasonHwThermalSlowdown',
+                 'sw_thermal_slowdown': 'nvmlClocksThrottleReasonSwThermalSlowdown',
+                 'sw_power_cap': 'nvmlClocksThrottleReasonSwPowerCap',
+                 'hw_power_brake': 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown'}
+        return {k for k, attr in names.items() if mask & getattr(nv, attr, 0)}
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reasons |= self._reasons(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def workload_config(a, n_per_gpu):
+    return {'workload': f'{a.env_id}, {n_per_gpu} lock-step envs per GPU, DR 0.10, observation noise on, '
+                        f'H=2, U(-1,1) actions, auto-reset (BASELINE.json configs[1])',
+            'env_id': a.env_id, 'envs_per_gpu': n_per_gpu, 'env_steps_per_bench_step': a.inner * n_per_gpu,
+            'inner_env_steps': a.inner, 'rng': 'philox4x32-10 on device',
+            'l2': 'actions and observations stream through ring buffers larger than L2; the per-env state '
+                  'is L2-resident at this size by the workload definition (see roofline_hbm_resident_off)'}
+
+
+# =============================================================================================
+#  GPU arm
+# =============================================================================================
+class Segment:
+    """One rollout segment: `inner` env.steps into [inner, N, .] tensors of a ring of segments."""
+
+    def __init__(self, env, inner, n_ring, gen):
+        import torch
+        n, d, dev = env.num_envs, env.obs_dim, env.device
+        self.env, self.inner, self.n_ring = env, inner, n_ring
+        self.actions = torch.rand((n_ring, inner, n, 4), device=dev, generator=gen) * 2 - 1
+        self.obs = torch.empty((n_ring, inner, n, d), dtype=env.dtype, device=dev)
+        self.reward = torch.empty((n_ring, inner, n), dtype=env.dtype, device=dev)
+        self.cost = torch.empty((n_ring, inner, n), dtype=env.dtype, device=dev)
+        self.terminated = torch.empty((n_ring, inner, n), dtype=torch.uint8, device=dev)
+        self.truncated = torch.empty((n_ring, inner, n), dtype=torch.uint8, device=dev)
+        self.outs = [[{'obs': self.obs[r, t], 'reward': self.reward[r, t], 'cost': self.cost[r, t],
+                       'terminated': self.terminated[r, t], 'truncated': self.truncated[r, t]}
+                      for t in range(inner)] for r in range(n_ring)]
+
+    def run(self, k):
+        r = k % self.n_ring
+        env, acts, outs = self.env, self.actions[r], self.outs[r]
+        for t in range(self.inner):
+            env.step(acts[t], out=outs[t])
+        return self.inner
+
+
+def ring_slots(bytes_per_segment):
+    return max(2, -(-2 * L2_BYTES // bytes_per_segment))
+
+
+def time_device(env, seg, K, W, dist_ctx):
+    """K segments timed with CUDA events on the launching stream; max over ranks."""
+    import torch
+    launches = 0
+    for k in range(W):
+        seg.run(k)
+        dist_ctx.reduce_stats(env)
+    dist_ctx.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        launches += seg.run(W + k)
+        dist_ctx.reduce_stats(env)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    dist_ctx.barrier()
+    return dist_ctx.max_over_ranks(ms), launches
+
+
+def time_e2e(env, inner, K, W, dist_ctx, gen_seed):
+    """Same metric through the public VecEnv API with HOST buffers: every env.step copies its
+    actions from pinned host memory, launches, and copies obs/reward/flags back to pinned host
+    memory; all of it inside the timed region."""
+    import torch
+    n, d = env.num_envs, env.obs_dim
+    g = torch.Generator().manual_seed(gen_seed)
+    h_act = (torch.rand((inner, n, 4), generator=g) * 2 - 1).pin_memory()
+    h_obs = torch.empty((n, d), dtype=env.dtype).pin_memory()
+    h_rew = torch.empty((n,), dtype=env.dtype).pin_memory()
+    h_flags = torch.empty((2, n), dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((n, 4), dtype=torch.float32, device=env.device)
+    d_flags = torch.empty((2, n), dtype=torch.uint8, device=env.device)
+    out = {'terminated': d_flags[0], 'truncated': d_flags[1]}
+    h2d = h_act[0].numel() * 4
+    d2h = h_obs.numel() * h_obs.element_size() + h_rew.numel() * h_rew.element_size() + h_flags.numel()
+
+    def one(t):
+        d_act.copy_(h_act[t], non_blocking=True)
+        obs, rew, _, _, _ = env.step(d_act, out=out)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_flags.copy_(d_flags, non_blocking=True)
+
+    for _ in range(W):
+        for t in range(inner):
+            one(t)
+    dist_ctx.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        for t in range(inner):
+            one(t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = dist_ctx.max_over_ranks(e0.elapsed_time(e1))
+    dist_ctx.barrier()
+    assert torch.isfinite(h_obs).all()
+    return ms, h2d * inner, d2h * inner
+
+
+class DistCtx:
+    def __init__(self, n_gpus):
+        import torch
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=self.device)
+            self.dist = dist
+        else:
+            self.dist = None
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if not self.dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_stats(self, env):
+        """Episode-return statistics all-reduce: the only cross-GPU traffic of the path, once per
+        rollout segment (replaces utils/mpi_tools.py:217-240)."""
+        if not self.dist:
+            return
+        from phoenix_drone_simulation_b200.rollout import allreduce_episode_stats
+        allreduce_episode_stats(env.stats, self.dist)
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured)'
+    except Exception:
+        return HBM_FALLBACK_GBS, 'B200_PROFILING.md fallback'
+
+
+def run_gpu_arm(a):
+    cpu = None
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if world == 1 and rank == 0 and not a.no_cpu_baseline:
+        # before CUDA is initialised (fork-safe); bounded sample of the same workload
+        v, cores, steps, wall = cpu_env_steps_per_sec(a.env_id, a.cpu_seconds)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{steps} env-steps of {a.env_id} (defaults, U(-1,1) actions, auto-reset) in '
+                         f'{wall:.1f} s wall: {cores} processes x one numpy oracle env each'}
+
+    import torch
+    from phoenix_drone_simulation_b200 import VecEnv
+    ctx = DistCtx(a.gpus)
+    assert ctx.world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={ctx.world} (launch with torchrun for N>1)'
+    dev = ctx.device
+    n = a.num_envs
+    env = VecEnv(a.env_id, n, device=dev, dtype=torch.float32, seed=a.seed, env_offset=ctx.rank * n)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + ctx.rank)
+    seg_bytes = a.inner * n * (16 + env.obs_dim * 4)
+    seg = Segment(env, a.inner, ring_slots(seg_bytes), gen)
+
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    ms, launches = time_device(env, seg, a.steps, a.warmup, ctx)
+    clocks = sampler.stop()
+    env_steps = a.steps * a.inner * n * ctx.world
+    value = env_steps / (ms * 1e-3)
+
+    # roofline of the dominant kernel (the fused step): algorithmic bytes per launch / mean duration
+    peak, peak_src = measured_peak()
+    bytes_per_launch = env.step_bytes * n
+    us_per_launch = ms * 1e3 / launches
+    achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'kernel': 'pdx::k_step<float, hover, simple, noise, philox>',
+                'bytes_per_env_step': env.step_bytes, 'us_per_launch': us_per_launch, 'peak_source': peak_src}
+
+    e2e_ms, h2d, d2h = time_e2e(env, a.inner, max(1, a.steps // a.e2e_div), a.warmup, ctx, 99 + ctx.rank)
+    e2e_steps = max(1, a.steps // a.e2e_div) * a.inner * n * ctx.world
+    e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'api': 'VecEnv.step with pinned host action/obs/reward/flag buffers, copies inside the timed region'}
+
+    extra = {}
+    if a.large_envs and ctx.world == 1:
+        # same kernel where the state cannot stay in L2: the honest HBM-bound measurement
+        nl = a.large_envs
+        big = VecEnv(a.env_id, nl, device=dev, dtype=torch.float32, seed=a.seed + 1)
+        big.reset()
+        inner_l = 4
+        segl = Segment(big, inner_l, 2, gen)
+        msl, ll = time_device(big, segl, max(4, a.steps // 8), 3, ctx)
+        usl = msl * 1e3 / ll
+        ach = big.step_bytes * nl / (usl * 1e-6) / 1e9
+        extra['roofline_hbm_resident_off'] = {
+            'envs': nl, 'state_bytes': int(big.state.numel() * 4), 'us_per_launch': usl, 'achieved': ach,
+            'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'env_steps_per_s': nl / (usl * 1e-6)}
+        del big, segl
+
+    stats = env.episode_stats().cpu().tolist()
+    ctx.close()
+    if ctx.rank != 0:
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a, n),
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        'episodes_finished': int(stats[0]),
+    }
+    if cpu:
+        line['cpu_baseline'] = cpu
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=100)
+    p.add_argument('--warmup', type=int, default=5)
+    p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    p.add_argument('--env-id', default=ENV_ID)
+    p.add_argument('--num-envs', type=int, default=65536, help='environments per GPU')
+    p.add_argument('--inner', type=int, default=64, help='env.steps per bench step (rollout segment)')
+    p.add_argument('--seed', type=int, default=0)
+    p.add_argument('--cpu-seconds', type=float, default=10.0)
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--e2e-div', type=int, default=4, help='e2e leg times steps/e2e_div segments')
+    p.add_argument('--large-envs', type=int, default=4 * 1024 * 1024)
+    a = p.parse_args()
+    if a.impl == 'reference':
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == '__main__':
+    main()

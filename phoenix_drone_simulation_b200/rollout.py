@@ -1,0 +1,263 @@
+"""Device-side PPO rollout collection for the batched engine.
+
+What each piece restates (reference paths relative to phoenix_drone_simulation/):
+  ActorCritic        algs/core.py:313-411  (pi 50-50 relu Gaussian, v 64-64 tanh, ppo/defaults.py:6-19;
+                     obs standardisation online_mean_std.py:32-48; std annealing core.py:268-276)
+  RolloutCollector   algs/iwpg/iwpg.py:350-385 (roll_out) + algs/core.py:481-557 (Buffer) for N
+                     lock-step environments: observations never leave device memory, every field
+                     is stored time-major in [T, N, .] tensors by the step kernel itself.
+  compute_gae        algs/core.py:458-479,497-534 (finish_path) -> CUDA kernel pdx_gae
+  OnlineMeanStd      utils/online_mean_std.py:50-95 incl. its non-textbook variance update;
+                     the cross-rank averages (mpi_tools.py:199-214) become NCCL all-reduces
+  EpisodeStats /     utils/loggers.py:519-524 + mpi_tools.py:217-240 (mean/std/min/max of
+  allreduce_episode_stats   EpRet / EpLen across ranks) from the block-reduced sums of the step kernel
+
+Cross-GPU traffic: two small all-reduces per rollout for the episode statistics and two per
+`OnlineMeanStd.update` -- nothing on the env.step itself.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as _lib
+
+
+def _world(dist):
+    return dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+
+
+# ---------------------------------------------------------------------------------------------
+#  episode statistics
+# ---------------------------------------------------------------------------------------------
+def allreduce_episode_stats(stats, dist):
+    """In-place all-reduce of the 8-word statistics vector of VecEnv
+    [n, sum ret, sum ret^2, sum len, min ret, max ret, min len, max len] (float64):
+    one SUM over the first four words, one MAX over (-min, max) pairs."""
+    if _world(dist) == 1:
+        return stats
+    dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM)
+    ext = stats[4:] * stats.new_tensor([-1.0, 1.0, -1.0, 1.0])
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX)
+    stats[4:] = ext * stats.new_tensor([-1.0, 1.0, -1.0, 1.0])
+    return stats
+
+
+class EpisodeStats:
+    """mean / std / min / max of EpRet and mean of EpLen like EpochLogger.get_stats."""
+
+    def __init__(self, stats):
+        s = [float(v) for v in stats.detach().cpu().tolist()]
+        self.n = int(s[0])
+        if self.n:
+            self.ret_mean = s[1] / s[0]
+            self.ret_std = math.sqrt(max(s[2] / s[0] - self.ret_mean ** 2, 0.0))   # mpi_tools.py:233
+            self.ret_min, self.ret_max = s[4], s[5]
+            self.len_mean, self.len_min, self.len_max = s[3] / s[0], s[6], s[7]
+        else:
+            self.ret_mean = self.ret_std = self.ret_min = self.ret_max = float('nan')
+            self.len_mean = self.len_min = self.len_max = float('nan')
+
+    def as_dict(self):
+        return {'EpRet/Mean': self.ret_mean, 'EpRet/Std': self.ret_std, 'EpRet/Min': self.ret_min,
+                'EpRet/Max': self.ret_max, 'EpLen/Mean': self.len_mean, 'Episodes': self.n}
+
+
+# ---------------------------------------------------------------------------------------------
+#  running mean / std
+# ---------------------------------------------------------------------------------------------
+def column_moments(x, shift=None):
+    """sum_r x[r, :] and sum_r (x[r, :] - shift)^2 in float64 (CUDA kernel pdx_moments)."""
+    if not x.is_cuda:
+        raise _lib.PhoenixB200Error('column_moments needs CUDA tensors: there is no CPU fallback')
+    x = x.reshape(-1, x.shape[-1]).contiguous().float()
+    rows, dim = x.shape
+    out = torch.zeros(2 * dim, dtype=torch.float64, device=x.device)
+    sp = None
+    if shift is not None:
+        shift = shift.to(device=x.device, dtype=torch.float64).contiguous()
+        sp = C.c_void_p(shift.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(_lib.load().pdx_moments(rows, dim, C.c_void_p(x.data_ptr()), sp, C.c_void_p(out.data_ptr()), st))
+    return out[:dim], out[dim:]
+
+
+class OnlineMeanStd:
+    """Running mean/std with the reference's update rule (online_mean_std.py:70-95):
+    n_B = rows * P; the batch mean is the plain average of the per-rank means; the batch second
+    moment is taken about the NEW mean and delta^2 n_A n_B / n_AB is added on top."""
+
+    def __init__(self, dim, device, epsilon=1e-5, dist=None, moments_fn=column_moments):
+        self.mean = torch.zeros(dim, dtype=torch.float32, device=device)
+        self.std = torch.ones(dim, dtype=torch.float32, device=device)
+        self.count = torch.zeros(1, dtype=torch.float32, device=device)
+        self.eps, self.bound, self.dist = epsilon, 10.0, dist
+        self._moments = moments_fn
+
+    def __call__(self, x, subtract_mean=True, clip=False):
+        y = (x - self.mean) / (self.std + self.eps) if subtract_mean else x / (self.std + self.eps)
+        return torch.clamp(y, -self.bound, self.bound) if clip else y
+
+    def _avg(self, t):                                   # mpi_tools.mpi_avg_torch_tensor
+        P = _world(self.dist)
+        if P > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            t /= P
+        return t
+
+    def update(self, x):
+        x = x.reshape(-1, self.mean.shape[0])
+        rows = x.shape[0]
+        n_B = float(rows * _world(self.dist))
+        n_A = self.count.clone()
+        n_AB = self.count + n_B
+        s1, _ = self._moments(x, None)
+        batch_mean = self._avg((s1 / rows).float())
+        delta = batch_mean - self.mean
+        mean_new = self.mean + delta * n_B / n_AB
+        _, s2 = self._moments(x, mean_new.double())
+        batch_var = self._avg((s2 / rows).float())
+        M2 = n_A * self.std ** 2 + n_B * batch_var + delta ** 2 * (n_A * n_B / n_AB)
+        self.mean, self.count = mean_new, n_AB
+        self.std = torch.sqrt(M2 / n_AB)
+
+    def state_dict(self):
+        return {'mean': self.mean.clone(), 'std': self.std.clone(), 'count': self.count.clone()}
+
+    def load_state_dict(self, sd):
+        self.mean.copy_(sd['mean']); self.std.copy_(sd['std']); self.count.copy_(sd['count'])
+
+
+# ---------------------------------------------------------------------------------------------
+#  GAE
+# ---------------------------------------------------------------------------------------------
+def compute_gae(rew, val, done, boot_val, last_val, gamma=0.99, lam=0.95, ret_std=None, eps=1e-5):
+    """Buffer.finish_path for a [T, N] lock-step rollout (CUDA kernel pdx_gae).
+    done: uint8, 1 = terminated (v=0), 2 = time limit (bootstrap with boot_val[t]).  `ret_std`:
+    running std of the discounted returns -> reward scaling r / (std + eps) clipped to +-10.
+    Returns (adv, target_v, discounted_ret), float32 [T, N]."""
+    if not rew.is_cuda:
+        raise _lib.PhoenixB200Error('compute_gae needs CUDA tensors: there is no CPU fallback')
+    T, n = rew.shape
+    f = lambda t: t.contiguous().float()
+    rew, val, boot_val, last_val = f(rew), f(val), f(boot_val), f(last_val)
+    done = done.contiguous().to(torch.uint8)
+    adv, tv, dr = torch.empty_like(rew), torch.empty_like(rew), torch.empty_like(rew)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream(rew.device).cuda_stream)
+    scale = float(ret_std) + eps if ret_std is not None else 1.0
+    _lib.check(_lib.load().pdx_gae(T, n, p(rew), p(val), p(done), p(boot_val), p(last_val), gamma, lam,
+                                   scale, 1 if ret_std is not None else 0, p(adv), p(tv), p(dr), st))
+    return adv, tv, dr
+
+
+# ---------------------------------------------------------------------------------------------
+#  actor-critic (the reference's PPO networks)
+# ---------------------------------------------------------------------------------------------
+def _mlp(sizes, act):
+    layers = []
+    for j in range(len(sizes) - 1):
+        lin = torch.nn.Linear(sizes[j], sizes[j + 1])
+        torch.nn.init.kaiming_uniform_(lin.weight, a=math.sqrt(5))          # core.py:34-35
+        layers += [lin, act() if j < len(sizes) - 2 else torch.nn.Identity()]
+    return torch.nn.Sequential(*layers)
+
+
+class ActorCritic(torch.nn.Module):
+    def __init__(self, obs_dim, act_dim=4, pi_hidden=(50, 50), v_hidden=(64, 64), device='cuda',
+                 use_standardized_obs=True, use_scaled_rewards=True, dist=None):
+        super().__init__()
+        self.pi = _mlp([obs_dim, *pi_hidden, act_dim], torch.nn.ReLU)
+        self.v = _mlp([obs_dim, *v_hidden, 1], torch.nn.Tanh)
+        self.log_std = torch.nn.Parameter(torch.full((act_dim,), math.log(0.5)), requires_grad=False)
+        self.to(device)
+        self.obs_oms = OnlineMeanStd(obs_dim, device, dist=dist) if use_standardized_obs else None
+        self.ret_oms = OnlineMeanStd(1, device, dist=dist) if use_scaled_rewards else None
+
+    def set_log_std(self, frac):                                              # core.py:268-276
+        self.log_std.fill_(math.log(0.499 * frac + 0.01))
+
+    @torch.no_grad()
+    def value(self, obs):
+        o = obs.float()
+        if self.obs_oms:
+            o = self.obs_oms(o)
+        return self.v(o).squeeze(-1)
+
+    @torch.no_grad()
+    def step(self, obs, generator=None):
+        """obs [N, D] on device -> (action [N, 4], value [N], logp [N]), all on device."""
+        o = obs.float()
+        if self.obs_oms:
+            o = self.obs_oms(o)
+        v = self.v(o).squeeze(-1)
+        mu = self.pi(o)
+        std = torch.exp(self.log_std)
+        eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=generator)
+        a = mu + std * eps
+        logp = (-0.5 * eps ** 2 - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        return a, v, logp
+
+
+# ---------------------------------------------------------------------------------------------
+#  collector
+# ---------------------------------------------------------------------------------------------
+class RolloutCollector:
+    """roll_out() of IWPGAlgorithm for a VecEnv: T lock-step steps of N environments.
+
+    reset_each_rollout=True is the reference's behaviour (the env is reset at the start of every
+    roll_out and episodes never span epochs, iwpg.py:353,375); False lets episodes continue."""
+
+    def __init__(self, env, ac, steps, gamma=0.99, lam=0.95, reset_each_rollout=True, dist=None):
+        assert env.final_obs is not None, 'construct the VecEnv with keep_final_obs=True'
+        self.env, self.ac, self.T, self.gamma, self.lam = env, ac, int(steps), gamma, lam
+        self.reset_each_rollout, self.dist = reset_each_rollout, dist
+        n, d, dev, T = env.num_envs, env.obs_dim, env.device, self.T
+        self.obs = torch.zeros((T + 1, n, d), dtype=env.dtype, device=dev)
+        self.act = torch.zeros((T, n, 4), dtype=torch.float32, device=dev)
+        self.rew = torch.zeros((T, n), dtype=env.dtype, device=dev)
+        self.cost = torch.zeros((T, n), dtype=env.dtype, device=dev)
+        self.val = torch.zeros((T, n), dtype=torch.float32, device=dev)
+        self.logp = torch.zeros((T, n), dtype=torch.float32, device=dev)
+        self.term = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+        self.boot = torch.zeros((T, n), dtype=torch.float32, device=dev)
+        self._outs = [{'obs': self.obs[t + 1], 'reward': self.rew[t], 'cost': self.cost[t],
+                       'terminated': self.term[t], 'truncated': self.trunc[t]} for t in range(T)]
+        self._started = False
+
+    def collect(self, generator=None):
+        env, ac, T = self.env, self.ac, self.T
+        if self.reset_each_rollout or not self._started:
+            self.obs[0].copy_(env.reset())
+            self._started = True
+        else:
+            self.obs[0].copy_(self.obs[T])
+        env.clear_episode_stats()
+        self.boot.zero_()
+        limit = env.max_episode_steps
+        for t in range(T):
+            a, v, logp = ac.step(self.obs[t], generator)
+            self.act[t], self.val[t], self.logp[t] = a, v, logp
+            env.step(self.act[t], out=self._outs[t])
+            # time-limit truncation needs V(last observation of the episode); the engine only
+            # truncates when an episode reaches max_episode_steps, i.e. not before step `limit`
+            if (not self.reset_each_rollout) or t + 1 >= limit or env.cfg.reset_on_nonfinite:
+                self.boot[t] = ac.value(env.final_obs) * self.trunc[t].float()
+        last_val = ac.value(self.obs[T])
+        # iwpg.py:371-380: a time-limit hit bootstraps even if the env also terminated
+        done = torch.where(self.trunc > 0, torch.full_like(self.term, 2), self.term)
+        ret_std = ac.ret_oms.std if ac.ret_oms is not None else None
+        adv, target_v, disc_ret = compute_gae(self.rew, self.val, done, self.boot, last_val, self.gamma,
+                                              self.lam, ret_std.item() if ret_std is not None else None)
+        stats = allreduce_episode_stats(env.episode_stats(), self.dist)
+        return {'obs': self.obs[:T], 'act': self.act, 'adv': adv, 'target_v': target_v, 'log_p': self.logp,
+                'discounted_ret': disc_ret, 'rew': self.rew, 'val': self.val, 'done': done,
+                'episode_stats': EpisodeStats(stats)}
+
+    def update_running_statistics(self, data):
+        """iwpg.py:387-396: after the update phase, on the raw observations / discounted returns."""
+        if self.ac.obs_oms is not None:
+            self.ac.obs_oms.update(data['obs'])
+        if self.ac.ret_oms is not None:
+            self.ac.ret_oms.update(data['discounted_ret'].reshape(-1, 1))

@@ -132,14 +132,31 @@ class VecEnv:
                                       self._next_counter(), self._stream()))
         return self.obs
 
-    def step(self, actions):
+    def step(self, actions, out=None):
         """actions: float32 CUDA tensor [N, 4].  Returns (obs, reward, terminated, truncated,
-        info); the tensors are owned by the VecEnv and overwritten by the next call."""
+        info); the tensors are owned by the VecEnv and overwritten by the next call.
+
+        `out` (optional): dict of caller-owned CUDA tensors that receive this step's results
+        instead -- keys 'obs' [N, D], 'reward' [N], 'cost' [N] (engine dtype), 'terminated' [N],
+        'truncated' [N] (uint8); missing keys fall back to the VecEnv's own buffers.  This is how
+        the rollout collector stores straight into its [T, N, .] tensors."""
         if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert actions.shape == (self.num_envs, 4)
-        _lib.check(self.lib.pdx_step(C.byref(self.pdx), C.byref(self._buf), C.c_void_p(actions.data_ptr()),
+        buf = self._buf
+        if out:
+            buf = _lib.PdxBuffers.from_buffer_copy(self._buf)
+            for k, t in out.items():
+                assert t.is_cuda and t.is_contiguous() and t.shape[0] == self.num_envs, k
+                setattr(buf, k, t.data_ptr())
+        _lib.check(self.lib.pdx_step(C.byref(self.pdx), C.byref(buf), C.c_void_p(actions.data_ptr()),
                                      self.seed, self._next_counter(), self._stream()))
+        if out:
+            return (out.get('obs', self.obs), out.get('reward', self.reward),
+                    out['terminated'].view(torch.bool) if 'terminated' in out else self.terminated,
+                    out['truncated'].view(torch.bool) if 'truncated' in out else self.truncated,
+                    {'cost': out.get('cost', self.cost), 'episode_return': self.episode_return,
+                     'episode_length': self.episode_length})
         info = {'cost': self.cost, 'episode_return': self.episode_return,
                 'episode_length': self.episode_length}
         if self.final_obs is not None:

@@ -1,0 +1,126 @@
+"""GPU tests of the rollout-collector kernels (pdx_gae, pdx_moments) and of the device-side
+collector, against oracle/collector_oracle.py and the reference's golden vectors
+(tests/golden_collector).  float32 arithmetic: tolerance 2e-4 relative / absolute (the kernel walks
+time backwards in float32 like scipy.lfilter does, summation order identical, FMA contraction
+allowed)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import collector_oracle as co
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden_collector')
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    return {k: z[k] for k in z.files}
+
+
+def _cuda(x):
+    return torch.as_tensor(x, device='cuda')
+
+
+@pytest.mark.parametrize('name', ['gae_scaled', 'gae_plain'])
+def test_gae_kernel_matches_reference_golden(name):
+    from phoenix_drone_simulation_b200.rollout import compute_gae
+    g = _load(name)
+    ret_std = float(g['ret_std'][0]) if bool(g['scaled']) else None
+    col = lambda k: _cuda(g[k])[:, None].repeat(1, 5).contiguous()
+    adv, tv, dr = compute_gae(col('rew'), col('val'), col('done'), col('boot_val'),
+                              _cuda(np.full(5, g['last_val'], np.float32)), 0.99, 0.95, ret_std)
+    for got, ref in ((adv, g['adv']), (tv, g['target_v']), (dr, g['disc_ret'])):
+        for c in range(5):
+            np.testing.assert_allclose(got[:, c].cpu().numpy(), ref, rtol=2e-4, atol=2e-4)
+
+
+def test_gae_kernel_matches_oracle_on_random_rollout():
+    from phoenix_drone_simulation_b200.rollout import compute_gae
+    rng = np.random.default_rng(7)
+    T, N = 70, 300
+    rew = rng.normal(-1, 2, (T, N)).astype(np.float32)
+    val = rng.normal(-5, 3, (T, N)).astype(np.float32)
+    u = rng.random((T, N))
+    done = np.where(u < 0.05, 1, np.where(u < 0.08, 2, 0)).astype(np.uint8)
+    boot = (rng.normal(-5, 3, (T, N)) * (done == 2)).astype(np.float32)
+    last = rng.normal(-5, 3, N).astype(np.float32)
+    for ret_std in (None, 17.5):
+        adv, tv, dr = compute_gae(_cuda(rew), _cuda(val), _cuda(done), _cuda(boot), _cuda(last), 0.99, 0.95, ret_std)
+        a0, t0, d0 = co.rollout_gae(rew, val, done, boot, last, 0.99, 0.95, ret_std)
+        np.testing.assert_allclose(adv.cpu().numpy(), a0, rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(tv.cpu().numpy(), t0, rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(dr.cpu().numpy(), d0, rtol=2e-4, atol=2e-4)
+
+
+def test_moments_kernel():
+    from phoenix_drone_simulation_b200.rollout import column_moments
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for rows, dim in ((1, 1), (1000, 34), (4097, 160), (65536, 48), (333, 1)):
+        x = torch.randn((rows, dim), device='cuda', generator=g) * 3 + 1
+        sh = torch.randn(dim, device='cuda', generator=g, dtype=torch.float64)
+        s1, s2 = column_moments(x, sh)
+        xd = x.double()
+        torch.testing.assert_close(s1, xd.sum(0), rtol=1e-10, atol=1e-8)
+        torch.testing.assert_close(s2, ((xd - sh) ** 2).sum(0), rtol=1e-10, atol=1e-8)
+        s1b, s2b = column_moments(x, None)
+        torch.testing.assert_close(s2b, (xd ** 2).sum(0), rtol=1e-10, atol=1e-8)
+
+
+@pytest.mark.parametrize('name', ['oms_obs34', 'oms_ret1'])
+def test_online_mean_std_on_device_matches_reference(name):
+    from phoenix_drone_simulation_b200.rollout import OnlineMeanStd
+    g = _load(name)
+    dim = g['x'].shape[2]
+    oms = OnlineMeanStd(dim, 'cuda')
+    for b in range(g['x'].shape[0]):
+        oms.update(_cuda(g['x'][b]))
+        np.testing.assert_allclose(oms.mean.cpu().numpy(), g['mean'][b], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(oms.std.cpu().numpy(), g['std'][b], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(oms.count.cpu().numpy(), g['count'][b])
+    np.testing.assert_allclose(oms(_cuda(g['probe'])).cpu().numpy(), g['forward'], rtol=1e-4, atol=1e-5)
+
+
+def test_collector_end_to_end_config5():
+    """BASELINE config 5: DroneHoverBulletEnv-v0 driving a PPO rollout (reference networks), all on
+    device.  Checks the stored fields against an independent recomputation."""
+    from phoenix_drone_simulation_b200 import VecEnv
+    from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
+    torch.manual_seed(0)
+    N, T = 2048, 48
+    env = VecEnv('DroneHoverBulletEnv-v0', N, seed=5, keep_final_obs=True)
+    ac = ActorCritic(env.obs_dim, device='cuda')
+    col = RolloutCollector(env, ac, T)
+    data = col.collect()
+    assert data['obs'].shape == (T, N, env.obs_dim) and data['act'].shape == (T, N, 4)
+    for k in ('obs', 'act', 'adv', 'target_v', 'log_p', 'discounted_ret'):
+        assert torch.isfinite(data[k]).all(), k
+    # values / log-probs are those of the stored (obs, act)
+    v = ac.value(data['obs'][7])
+    torch.testing.assert_close(v, data['val'][7], rtol=1e-5, atol=1e-5)
+    mu = ac.pi(ac.obs_oms(data['obs'][7].float()))
+    logp = torch.distributions.Normal(mu, torch.exp(ac.log_std)).log_prob(data['act'][7]).sum(-1)
+    torch.testing.assert_close(logp, data['log_p'][7], rtol=1e-4, atol=1e-4)
+    # GAE of a few columns against the oracle
+    done = data['done'].cpu().numpy()
+    last_val = ac.value(col.obs[T]).cpu().numpy()
+    cols = [0, 5, 777, N - 1]
+    a0, t0, d0 = co.rollout_gae(data['rew'].float().cpu().numpy()[:, cols], data['val'].cpu().numpy()[:, cols],
+                                done[:, cols], col.boot.cpu().numpy()[:, cols], last_val[cols], 0.99, 0.95,
+                                float(ac.ret_oms.std))
+    np.testing.assert_allclose(data['adv'].cpu().numpy()[:, cols], a0, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(data['discounted_ret'].cpu().numpy()[:, cols], d0, rtol=2e-4, atol=2e-4)
+    # episode statistics = what the flags say
+    es = data['episode_stats']
+    assert es.n == int((done != 0).sum())
+    if es.n:
+        assert es.ret_min <= es.ret_mean <= es.ret_max and 1 <= es.len_min <= es.len_max <= T
+    # running statistics update (two moment passes on device)
+    col.update_running_statistics(data)
+    o = data['obs'].reshape(-1, env.obs_dim).float()
+    torch.testing.assert_close(ac.obs_oms.mean, o.mean(0), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(ac.obs_oms.std, o.std(0, unbiased=False), rtol=1e-3, atol=1e-4)
+    data2 = col.collect()           # second rollout uses the updated normaliser
+    assert torch.isfinite(data2['adv']).all()
