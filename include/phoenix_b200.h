@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PDX_ABI_VERSION 3
+#define PDX_ABI_VERSION 4
 
 typedef enum PdxStatus {
   PDX_OK = 0,
@@ -141,13 +141,15 @@ int         pdx_config_finalize(PdxConfig* cfg);
 int         pdx_state_quads(const PdxConfig* cfg);       /* planes of 4 reals per env */
 /* Location of a named state field ("xyz","vel","rpy","omega","quat","omega_world","dt",
  * "mass","inertia","ftf1","motor_a","motor_k","motor_x","ring","ring_idx","ou",
- * "gyro_bias","gyro_lpf","last_action","env_last_action","ep_return","ep_length",
- * "iteration","ref_offset","hist").  Writes the first word index (quad*4+lane) and the
+ * "gyro_bias","gyro_lpf","last_action","ep_return","ep_length","ref_offset","hist").  Writes the first word index (quad*4+lane) and the
  * length in words; returns 0, or PDX_ERR_INVALID if the field does not exist. */
 int         pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int* n_words);
 int         pdx_tape_slots(const PdxConfig* cfg, int* reset_slots, int* step_slots, int* init_slots);
-/* Algorithmic HBM bytes one env.step moves (state read+write, action, obs, outputs). */
+/* Algorithmic HBM bytes per environment of one launch that advances n_steps env.steps: state and
+ * history read once and written once, plus per step the action in and the observation row,
+ * reward, cost and flags out.  pdx_step_bytes(cfg) == pdx_rollout_bytes(cfg, 1). */
 int64_t     pdx_step_bytes(const PdxConfig* cfg);
+int64_t     pdx_rollout_bytes(const PdxConfig* cfg, int32_t n_steps);
 
 /* ---- compute (CUDA; fail with PDX_ERR_NO_DEVICE / PDX_ERR_CUDA otherwise) ------------- */
 int pdx_device_count(void);
@@ -165,6 +167,15 @@ int pdx_reset(const PdxConfig* cfg, const PdxBuffers* buf, const uint8_t* mask,
  * float32 (the policy's dtype; the PWM stage quirk of control.py:98-99 depends on it). */
 int pdx_step(const PdxConfig* cfg, const PdxBuffers* buf, const float* actions,
              uint64_t seed, uint64_t counter, void* stream);
+/* n_steps env.steps of every environment in ONE launch (the rollout-collector form of
+ * roll_out's inner loop, algs/iwpg/iwpg.py:355-385, for open-loop action sequences): the state
+ * stays in registers between steps.  `actions` is [n_steps][n_envs][4]; every per-step output of
+ * PdxBuffers is time-major with n_steps leading: obs [n_steps][n_envs][obs_dim], reward / cost /
+ * terminated / truncated / episode_return / episode_length [n_steps][n_envs], final_obs
+ * [n_steps][n_envs][obs_dim]; tapes [n_steps][slots][n_envs].  Step t draws its random numbers
+ * at `counter + t`, so the caller advances its counter by n_steps.  pdx_step == n_steps 1. */
+int pdx_step_many(const PdxConfig* cfg, const PdxBuffers* buf, const float* actions, int32_t n_steps,
+                  uint64_t seed, uint64_t counter, void* stream);
 /* Debug/validation: runs pdx_init (init_tape != NULL), pdx_reset of all envs (actions ==
  * NULL, reset_tape != NULL) or pdx_step (actions != NULL; needs step_tape and reset_tape) with
  * the production Philox draws and additionally writes every draw consumed into tape layout

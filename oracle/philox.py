@@ -28,8 +28,8 @@ def philox4x32_10(ctr, key):
 
 
 # draw-site ids of csrc/pdx_math.cuh (DrawSite)
-SITE_SUBSTEP, SITE_FINAL_OBS, SITE_RESET, SITE_DR = 0, 40, 64, 72
-SITE_RESET_OBS1, SITE_RESET_OBS2, SITE_INIT = 76, 84, 96
+SITE_SUBSTEP, SITE_FINAL_OBS, SITE_RESET, SITE_DR = 0, 64, 80, 88
+SITE_RESET_OBS1, SITE_RESET_OBS2, SITE_INIT = 96, 104, 112
 
 
 def engine_raw(seed, env_index, counter, site):

@@ -13,10 +13,11 @@ LIB = os.path.join(HERE, 'libphoenix_b200.so')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-std=c++17', '-O3', '-lineinfo', '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
 # translation unit -> extra flags.  The float64 kernels are the parity instantiation: no FMA
-# contraction, so that products and sums round like the reference's numpy expressions.
+# contraction, so that products and sums round like the reference's numpy expressions.  The
+# float32 kernels are the throughput instantiation: MUFU approximations for sin/cos/sqrt/div.
 UNITS = {
-    'pdx_tu_f32_simple.cu': [],
-    'pdx_tu_f32_bullet.cu': [],
+    'pdx_tu_f32_simple.cu': ['-use_fast_math'],
+    'pdx_tu_f32_bullet.cu': ['-use_fast_math'],
     'pdx_tu_f64_simple.cu': ['-fmad=false'],
     'pdx_tu_f64_bullet.cu': ['-fmad=false'],
     'pdx_abi.cu': [],

@@ -53,7 +53,7 @@ int check_buffers(const PdxConfig* c, const PdxBuffers* b, bool step) {
 
 int launch(int kind, const PdxConfig* cfg, const PdxBuffers* buf, const float* actions,
            const uint8_t* mask, uint64_t seed, uint64_t counter, double* ds, double* dr, double* di,
-           void* stream) {
+           void* stream, int n_steps = 1) {
   int rc = validate(cfg);
   if (rc) return rc;
   PdxConfig c = *cfg;
@@ -69,6 +69,7 @@ int launch(int kind, const PdxConfig* cfg, const PdxBuffers* buf, const float* a
     if (kind == pdx::KIND_INIT && ts.init && !buf->tape_init) return fail(PDX_ERR_INVALID, "tape mode needs tape_init");
   }
   if (kind == pdx::KIND_STEP && !actions) return fail(PDX_ERR_INVALID, "null actions");
+  if (kind == pdx::KIND_STEP && (n_steps < 1 || n_steps > (1 << 20))) return fail(PDX_ERR_INVALID, "n_steps must be in [1, 2^20]");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess) return cuda_fail(e);
@@ -76,7 +77,7 @@ int launch(int kind, const PdxConfig* cfg, const PdxBuffers* buf, const float* a
   if (buf->device < 0 || buf->device >= ndev) return fail(PDX_ERR_INVALID, "bad device ordinal");
   e = cudaSetDevice(buf->device);       // this library carries its own (static) CUDA runtime
   if (e != cudaSuccess) return cuda_fail(e);
-  pdx::LaunchArgs la{&c, buf, actions, mask, seed, counter, ds, dr, di, (cudaStream_t)stream};
+  pdx::LaunchArgs la{&c, buf, actions, mask, seed, counter, ds, dr, di, n_steps, (cudaStream_t)stream};
   if (c.dtype == PDX_DTYPE_F32)
     e = c.physics == PDX_PHYSICS_SIMPLE ? pdx::launch_f32_simple(kind, la) : pdx::launch_f32_bullet(kind, la);
   else
@@ -118,7 +119,7 @@ int pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int
       {"inertia", L.inertia, 3}, {"ftf1", L.ftf1, 1}, {"motor_b", L.motor_b, 4},
       {"motor_k", L.motor_k, 4}, {"motor_x", L.motor_x, 4}, {"ring", L.ring, 8},
       {"ring_idx", L.ring_idx, 1}, {"ou", L.ou, 4}, {"last_action", L.last_action, 4},
-      {"ep_return", L.ep_return, 1}, {"ep_length", L.ep_length, 1}, {"hist_phase", L.hist_phase, 1},
+      {"ep_return", L.ep_return, 1}, {"ep_length", L.ep_length, 1},
       {"ref_offset", L.ref_offset, 1}, {"gyro_bias", L.gyro_bias, 3}, {"gyro_lpf", L.gyro_lpf, 3},
       {"hist", L.n_quads * 4, (cfg->history - 1) * L.hist_quads * 4},
   };
@@ -142,15 +143,18 @@ int pdx_tape_slots(const PdxConfig* cfg, int* reset_slots, int* step_slots, int*
   return PDX_OK;
 }
 
-int64_t pdx_step_bytes(const PdxConfig* cfg) {
-  if (validate(cfg)) return PDX_ERR_INVALID;
+int64_t pdx_step_bytes(const PdxConfig* cfg) { return pdx_rollout_bytes(cfg, 1); }
+
+int64_t pdx_rollout_bytes(const PdxConfig* cfg, int32_t n_steps) {
+  if (validate(cfg) || n_steps < 1) return PDX_ERR_INVALID;
   const pdx::Layout L = layout_of(cfg);
   const int64_t sz = cfg->dtype == PDX_DTYPE_F32 ? 4 : 8;
   const int64_t E = L.core_dim + 4, H = cfg->history;
-  const int64_t read_words = L.n_words + (H - 1) * E;             // state + history ring
-  const int64_t write_words = L.n_dyn_words + (H > 1 ? E : 0);    // per-step words + newest entry
-  const int64_t obs = H * E;
-  return (read_words + write_words + obs + 2 /* reward, cost */) * sz + 16 /* action */ + 2 /* flags */;
+  // per launch: state + history read once and written once; per step: action in, observation
+  // row, reward, cost and the two flag bytes out.
+  const int64_t once = (L.n_words + (H - 1) * E) * sz + (L.n_words + (H - 1) * E) * sz;
+  const int64_t per_step = (H * E + 2) * sz + 16 + 2;
+  return once + per_step * n_steps;
 }
 
 int pdx_device_count(void) {
@@ -172,6 +176,11 @@ int pdx_reset(const PdxConfig* cfg, const PdxBuffers* buf, const uint8_t* mask, 
 int pdx_step(const PdxConfig* cfg, const PdxBuffers* buf, const float* actions, uint64_t seed,
              uint64_t counter, void* stream) {
   return launch(pdx::KIND_STEP, cfg, buf, actions, nullptr, seed, counter, nullptr, nullptr, nullptr, stream);
+}
+
+int pdx_step_many(const PdxConfig* cfg, const PdxBuffers* buf, const float* actions, int32_t n_steps,
+                  uint64_t seed, uint64_t counter, void* stream) {
+  return launch(pdx::KIND_STEP, cfg, buf, actions, nullptr, seed, counter, nullptr, nullptr, nullptr, stream, n_steps);
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@ struct LaunchArgs {
   double* dump_step;
   double* dump_reset;
   double* dump_init;
+  int n_steps;
   cudaStream_t stream;
 };
 
@@ -30,6 +31,7 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
   d.dr_on = p.domain_randomization > 0 ? 1 : 0; d.reset_on_nonfinite = p.reset_on_nonfinite; d.auto_reset = p.auto_reset;
   d.slots_obs_full = ts.obs_full; d.slots_obs_gyro = ts.obs_gyro;
   d.slots_reset_task = ts.reset_task; d.slots_reset_dr = ts.reset_dr;
+  d.slots_step = ts.step; d.slots_reset = ts.reset;
   d.dr = (T)p.domain_randomization; d.time_step = (T)p.time_step; d.mass = (T)p.mass;
   for (int k = 0; k < 3; ++k) {
     d.inertia[k] = (T)p.inertia[k]; d.target[k] = (T)p.target_pos[k];
@@ -53,13 +55,39 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
   d.ground_z = (T)p.ground_z;
 }
 
+// Threads per block of k_rollout: as large as the shared-memory plan allows (<= 128 so that a
+// 65,536-env shard still spreads over all 148 SMs), never below one warp.
+template <class T>
+static int pick_block(int D, int NW, int C) {
+  int block = 128;
+  while (block > 32 && rollout_smem_bytes<T>(block, D, NW, C) > (size_t)200 * 1024) block >>= 1;
+  return block;
+}
+
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
 static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
+  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   const int64_t n = ka.b.n_envs;
-  const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
-  if (kind == KIND_INIT) k_init<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
-  else if (kind == KIND_RESET) k_reset<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
-  else k_step<T, TASK, PHYS, NOISE, RNG><<<grid, kBlock, 0, st>>>(ka);
+  if (kind != KIND_STEP) {
+    const int block = 128;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    if (kind == KIND_INIT) k_init<T, TASK, PHYS, NOISE, RNG><<<grid, block, 0, st>>>(ka);
+    else k_reset<T, TASK, PHYS, NOISE, RNG><<<grid, block, 0, st>>>(ka);
+    return cudaGetLastError();
+  }
+  const int block = pick_block<T>(ka.c.obs_dim, Mo::NW, Mo::C);
+  const size_t smem = rollout_smem_bytes<T>(block, ka.c.obs_dim, Mo::NW, Mo::C);
+  if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
+  static size_t smem_set[16] = {0};                 // per device: opt-in dynamic shared memory
+  const int dev = ka.b.device & 15;
+  if (smem > smem_set[dev]) {
+    const cudaError_t e = cudaFuncSetAttribute(k_rollout<T, TASK, PHYS, NOISE, RNG>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set[dev] = smem;
+  }
+  const unsigned grid = (unsigned)((n + block - 1) / block);
+  k_rollout<T, TASK, PHYS, NOISE, RNG><<<grid, block, smem, st>>>(ka);
   return cudaGetLastError();
 }
 
@@ -81,6 +109,7 @@ static cudaError_t launch_tu(int kind, const LaunchArgs& la) {
   ka.b = *la.buf;
   ka.actions = la.actions; ka.mask = la.mask; ka.seed = la.seed; ka.counter = la.counter;
   ka.dump_step = la.dump_step; ka.dump_reset = la.dump_reset; ka.dump_init = la.dump_init;
+  ka.n_steps = la.n_steps;
   const bool noise = la.cfg->observation_noise != 0;
   // pdx_dump_draws runs the TAPE-mode kernels with dump pointers set.
   const int rng = (la.dump_step || la.dump_reset || la.dump_init) ? PDX_RNG_TAPE : la.cfg->rng_mode;

@@ -1,12 +1,24 @@
-// Kernels: init (constructor), reset (masked) and the fused step with in-kernel auto-reset.
-// One thread per environment; state quads are loaded once, kept in registers across all
-// physics sub-steps of the env.step and stored once.
+// Kernels: init (constructor), reset (masked) and the fused multi-step rollout kernel.
+//
+// k_rollout advances every environment by n_steps env.steps in ONE launch:
+//   * one thread owns one environment; its state quads are loaded once (coalesced 128-bit
+//     accesses), live in registers across all steps and sub-steps, and are stored once;
+//   * each step's observation rows are assembled in a shared-memory tile that has exactly the
+//     layout of the block's slice of the row-major [n_envs][obs_dim] output, and leave the SM
+//     as ONE bulk asynchronous copy (cp.async.bulk shared->global, the TMA engine; SASS UBLKCP)
+//     issued by one thread, double buffered so the copy of step t overlaps step t+1;
+//   * episodes that end are reset inside the same launch.  The reset path is long (two noisy
+//     observation calls, ~20 Philox calls), so finished environments of a block are compacted
+//     through shared memory and reset by the lanes of warp 0 instead of diverging every warp;
+//   * episode statistics are reduced by that warp with shuffles, one set of atomics per block
+//     and launch.
 #pragma once
 #include "pdx_model.cuh"
 
 namespace pdx {
 
-constexpr int kBlock = 128;
+constexpr int kMaxBlock = 256;     // threads per block are chosen at run time (<= kMaxBlock)
+constexpr int kSlots = 32;         // reset slots per pass = lanes of warp 0
 
 template <class T>
 struct KArgs {
@@ -18,17 +30,18 @@ struct KArgs {
   double* dump_step;
   double* dump_reset;
   double* dump_init;
+  int n_steps;
 };
 
 template <class T, int RNG>
-__device__ __forceinline__ Rng<T, RNG> make_rng(const KArgs<T>& a, int64_t i, const double* tape,
-                                                double* dump) {
+__device__ __forceinline__ Rng<T, RNG> make_rng(const KArgs<T>& a, uint64_t counter, int64_t i,
+                                                const double* tape, double* dump) {
   Rng<T, RNG> r;
   const uint64_t env = (uint64_t)(a.b.env_offset + i);
   r.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   r.env_lo = (uint32_t)env;
-  r.env_hi = (uint32_t)(env >> 32) ^ ((uint32_t)(a.counter >> 32) << 8);
-  r.ctr_lo = (uint32_t)a.counter;
+  r.env_hi = (uint32_t)(env >> 32) ^ ((uint32_t)(counter >> 32) << 8);
+  r.ctr_lo = (uint32_t)counter;
   r.tape = tape ? tape + i : nullptr;
   r.stride = a.b.n_envs;
   r.dump = dump ? dump + i : nullptr;
@@ -40,20 +53,20 @@ template <class T> __device__ __forceinline__ T f32q(T x) { return (T)(float)x; 
 template <class T> __device__ __forceinline__ T unif(T lo, T hi, T u) { return lo + (hi - lo) * u; }
 
 // ---------------------------------------------------------------------------------------------
-//  DroneBaseEnv.reset for one env.  Keeps OU state and gyro bias (never reset, quirk A.6-8).
+//  DroneBaseEnv.reset for one env (base.py:382-431).  `m` holds the state to reset: only the
+//  gyro bias (and, for the caller, the OU state) survive a reset (quirk A.6-8); `stale` are the
+//  body rates of the previous episode's last state (base.py:411, quirk A.6-5).
+//  Outputs: m.w (complete new state, OU words untouched), o1 / o2 = the two observation calls
+//  (base.py:420,429); the history is H-1 copies of (o1, last_action) and one (o2, last_action).
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
 __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, const Rng<T, RNG>& rng,
-                                       T* state, int64_t n, int64_t i, T* obs_row) {
+                                          const T stale[3], T* o1, T* o2) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
-  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
   const DevCfg<T>& c = m.c;
   T* w = m.w;
   const T pi = T(3.14159265358979323846);
-
-  T stale[3];
-  m.body_rates(stale);                                   // base.py:411 (quirk A.6-5)
 
   T la[4] = {T(0), T(0), T(0), T(0)};                    // drone.last_action = ring[-1]
   T ring[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
@@ -77,10 +90,7 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
     for (int k = 0; k < 4; ++k) { la[k] = T(-1); ring[k] = T(-1); ring[4 + k] = T(-1); }
   } else if (c.reset_distribution) {
     T u[14];
-    rng.template uniforms<4>(SITE_RESET + 0, 0, &u[0]);
-    rng.template uniforms<4>(SITE_RESET + 1, 4, &u[4]);
-    rng.template uniforms<4>(SITE_RESET + 2, 8, &u[8]);
-    rng.template uniforms<2>(SITE_RESET + 3, 12, &u[12]);
+    rng.template uniforms<14>(SITE_RESET, 0, u);
     T rpy[3];
     if constexpr (TASK == PDX_TASK_HOVER) {                        // hover.py:192-229
 #pragma unroll
@@ -113,13 +123,13 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
     const T yl = pi * T(20) / T(180);
     oms[2] = unif(-yl, yl, u[13]);
     quat_from_euler(rpy[0], rpy[1], rpy[2], q);
-    T z[4];
-    rng.template normals<4>(SITE_RESET + 4, 14, z);
+    T z[8];
+    rng.template normals<8>(SITE_RESET + 4, 14, z);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = c.hover_x + T(0.02) * z[k];
-    rng.template normals<4>(SITE_RESET + 5, 18, z);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ring[k] = clampT(c.hover_action + T(0.02) * z[k], T(-1), T(1));
+    for (int k = 0; k < 4; ++k) {
+      x[k] = c.hover_x + T(0.02) * z[k];
+      ring[k] = clampT(c.hover_action + T(0.02) * z[4 + k], T(-1), T(1));
+    }
     if (c.buf_size > 1) {
       rng.template normals<4>(SITE_RESET + 6, 22, z);
 #pragma unroll
@@ -143,25 +153,22 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
   // apply_domain_randomization: base.py:239-296, agents.py:208-224
   int slot = c.slots_reset_task;
   if (c.dr_on) {
-    T u[4];
     auto draw = [&](T v, T uu) { const T b = c.dr * v; return unif(v - b, v + b, uu); };
-    rng.template uniforms<4>(SITE_DR + 0, slot, u);
+    T u[15];
+    if (Mo::BULLET && c.use_motor_dynamics) rng.template uniforms<15>(SITE_DR, slot, u);
+    else rng.template uniforms<7>(SITE_DR, slot, u);
     w[L.dt] = draw(c.time_step, u[0]);
     w[L.mass] = draw(c.mass, u[1]);
     w[L.inertia] = draw(c.inertia[0], u[2]);
     w[L.inertia + 1] = draw(c.inertia[1], u[3]);
-    rng.template uniforms<3>(SITE_DR + 1, slot + 4, u);    // u[1]: ftf0 (cancels, unused)
-    w[L.inertia + 2] = draw(c.inertia[2], u[0]);
-    w[L.ftf1] = draw(c.ftf1, u[2]);
+    w[L.inertia + 2] = draw(c.inertia[2], u[4]);           // u[5]: ftf0 (cancels, unused)
+    w[L.ftf1] = draw(c.ftf1, u[6]);
     if constexpr (Mo::BULLET) if (c.use_motor_dynamics) {
-      T t2[4];
-      rng.template uniforms<4>(SITE_DR + 2, slot + 7, u);
-      rng.template uniforms<4>(SITE_DR + 3, slot + 11, t2);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const T Tm = M<T>::fmax(draw(c.motor_tc, u[k]), w[L.dt]);
+        const T Tm = M<T>::fmax(draw(c.motor_tc, u[7 + k]), w[L.dt]);
         w[L.motor_b + k] = w[L.dt] / Tm;
-        w[L.motor_k + k] = c.k_mass_dr * c.gravity * draw(c.thrust2weight, t2[k]) / T(4);  // quirk A.6-7
+        w[L.motor_k + k] = c.k_mass_dr * c.gravity * draw(c.thrust2weight, u[11 + k]) / T(4);  // quirk A.6-7
       }
     }
   }
@@ -192,37 +199,27 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
   w[L.ep_return] = T(0);
   w[L.ep_length] = T(0);
 
-  // two observation calls (base.py:420,429) and the history fill (base.py:424-427)
+  // two observation calls (base.py:420,429)
   T target[3] = {c.target[0], c.target[1], c.target[2]};
   if constexpr (TASK == PDX_TASK_CIRCLE) m.ref_point(ref_off % 300, target);
   if constexpr (TASK == PDX_TASK_TAKEOFF) m.ref_point(0, target);
-  T o1[C], o2[C];
   m.observe(rng, SITE_RESET_OBS1, slot, target, la, q, o1);
   m.observe(rng, SITE_RESET_OBS2, slot + c.slots_obs_full, target, la, q, o2);
-  const int H = c.history;
-  const int g = (int)w[L.hist_phase];
-  for (int j = 0; j < H; ++j) {
-    const bool newest = j == H - 1;
+}
+
+// history slots of the state <- H-1 entries, `entry(s, idx)` gives word idx of slot s
+template <class T, int E, int QH, class F>
+__device__ __forceinline__ void store_history(T* state, int64_t n, int64_t i, int first_quad, int H, F entry) {
+  for (int s = 0; s < H - 1; ++s) {
 #pragma unroll
-    for (int k = 0; k < C; ++k) obs_row[j * E + k] = newest ? o2[k] : o1[k];
+    for (int qd = 0; qd < QH; ++qd) {
+      T v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) obs_row[j * E + C + k] = la[k];
-  }
-  if (H > 1) {
-    const int newest_pos = (g + H - 2) % (H - 1);
-    for (int s = 0; s < H - 1; ++s) {
-      const bool nw = s == newest_pos;
-#pragma unroll
-      for (int qd = 0; qd < QH; ++qd) {
-        T v[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int idx = qd * 4 + l;
-          v[l] = idx < C ? (nw ? o2[idx < C ? idx : 0] : o1[idx < C ? idx : 0])
-                         : (idx < E ? la[idx - C < 4 ? idx - C : 0] : T(0));
-        }
-        store_quad(state, n, i, L.n_quads + s * QH + qd, v);
+      for (int l = 0; l < 4; ++l) {
+        const int idx = qd * 4 + l;
+        v[l] = idx < E ? entry(s, idx < E ? idx : 0) : T(0);
       }
+      store_quad(state, n, i, first_quad + s * QH + qd, v);
     }
   }
 }
@@ -231,7 +228,7 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
 //  constructor: zero state, nominal parameters, base.py:143's compute_observation()
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
-__global__ void __launch_bounds__(kBlock) k_init(const KArgs<T> a) {
+__global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
   const int64_t n = a.b.n_envs;
@@ -256,7 +253,7 @@ __global__ void __launch_bounds__(kBlock) k_init(const KArgs<T> a) {
     }
   }
   if constexpr (NOISE) {
-    const Rng<T, RNG> rng = make_rng<T, RNG>(a, i, a.b.tape_init, a.dump_init);
+    const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter, i, a.b.tape_init, a.dump_init);
     T z[3];
     rng.template normals<3>(SITE_INIT, 12, z);
 #pragma unroll
@@ -268,9 +265,14 @@ __global__ void __launch_bounds__(kBlock) k_init(const KArgs<T> a) {
   for (int qd = 0; qd < (c.history - 1) * Mo::QH; ++qd) store_quad(state, n, i, L.n_quads + qd, zero);
 }
 
+// ---------------------------------------------------------------------------------------------
+//  explicit reset of all / masked environments (dense: one thread per env)
+// ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
-__global__ void __launch_bounds__(kBlock) k_reset(const KArgs<T> a) {
+__global__ void __launch_bounds__(kMaxBlock) k_reset(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
+  constexpr Layout L = Mo::L;
+  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
   const int64_t n = a.b.n_envs;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -278,9 +280,24 @@ __global__ void __launch_bounds__(kBlock) k_reset(const KArgs<T> a) {
   Mo m(a.c);
   T* state = reinterpret_cast<T*>(a.b.state);
   m.load(state, n, i);
-  const Rng<T, RNG> rng = make_rng<T, RNG>(a, i, a.b.tape_reset, a.dump_reset);
-  reset_env(m, rng, state, n, i, reinterpret_cast<T*>(a.b.obs) + i * a.c.obs_dim);
+  const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter, i, a.b.tape_reset, a.dump_reset);
+  T stale[3], o1[C], o2[C];
+  m.body_rates(stale);
+  reset_env(m, rng, stale, o1, o2);
   m.store(state, n, i, true);
+  const int H = a.c.history;
+  const T* la = &m.w[L.last_action];
+  T* row = reinterpret_cast<T*>(a.b.obs) + i * a.c.obs_dim;
+  for (int j = 0; j < H; ++j) {
+    const bool newest = j == H - 1;
+#pragma unroll
+    for (int k = 0; k < C; ++k) row[j * E + k] = newest ? o2[k] : o1[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[j * E + C + k] = la[k];
+  }
+  store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) {
+    return idx < C ? (s == H - 2 ? o2[idx < C ? idx : 0] : o1[idx < C ? idx : 0]) : la[idx - C < 4 && idx >= C ? idx - C : 0];
+  });
 }
 
 // CAS-based min/max on doubles for the episode statistics
@@ -303,230 +320,364 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   }
 }
 
+// ---- bulk asynchronous copy shared -> global (TMA engine), bulk-group completion ------------
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Shared-memory plan of k_rollout (dynamic shared memory, in units of T):
+//   tile0, tile1 : [B][D]          observation rows of the block, layout == global slice
+//   slots        : [SW][kSlots]    reset hand-over, SW = NW + 2C words per slot (SoA over slots)
+//   park         : [NW][kSlots]    registers of the resetting lanes while they work for others
+// followed by   int  warp_cnt[kMaxBlock / 32];  double stats[8];
+template <class T>
+__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int NW, int C) {
+  size_t words = (size_t)2 * block * D + (size_t)(NW + 2 * C) * kSlots + (size_t)NW * kSlots;
+  size_t bytes = words * sizeof(T);
+  bytes = (bytes + 15) & ~(size_t)15;
+  return bytes + sizeof(int) * (kMaxBlock / 32) + 8 + sizeof(double) * 8;
+}
+
 // ---------------------------------------------------------------------------------------------
-//  fused env.step (+ auto-reset)
+//  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
-__global__ void __launch_bounds__(kBlock) k_step(const KArgs<T> a) {
+__global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
-  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
+  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH, NW = Mo::NW;
+  constexpr int SW = NW + 2 * C;
   const DevCfg<T>& c = a.c;
   const int64_t n = a.b.n_envs;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t block_base = (int64_t)blockIdx.x * B;
+  const int64_t i = block_base + tid;
   const bool valid = i < n;
+  const int rows = (int)min((int64_t)B, n - block_base);
+  const int D = c.obs_dim, H = c.history;
 
-  __shared__ double s_stats[8];
-  __shared__ int s_any;
-  if (a.b.episode_stats) {
-    if (threadIdx.x == 0) s_any = 0;
-    if (threadIdx.x < 8)
-      s_stats[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 6) ? 1e300 : (threadIdx.x == 5 || threadIdx.x == 7) ? -1e300 : 0.0;
-    __syncthreads();
-  }
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile0 = reinterpret_cast<T*>(smem_raw);
+  T* tile1 = tile0 + (size_t)B * D;
+  T* slots = tile1 + (size_t)B * D;
+  T* park = slots + SW * kSlots;
+  size_t off = ((size_t)(park + NW * kSlots - tile0) * sizeof(T) + 15) & ~(size_t)15;
+  int* s_warp_cnt = reinterpret_cast<int*>(smem_raw + off);
+  double* s_stats = reinterpret_cast<double*>(smem_raw + off + sizeof(int) * (kMaxBlock / 32) + 8);
+  if (tid < 8) s_stats[tid] = (tid == 4 || tid == 6) ? 1e300 : (tid == 5 || tid == 7) ? -1e300 : 0.0;
 
-  bool fin = false;
-  T ep_ret_out = T(0);
-  int ep_len_out = 0;
   Mo m(c);
   T* state = reinterpret_cast<T*>(a.b.state);
-  T* obs_row = nullptr;
-
+  T* my_row0 = tile0 + (size_t)tid * D;
+  T* my_row1 = tile1 + (size_t)tid * D;
   if (valid) {
-    T* w = m.w;
     m.load(state, n, i);
-    const float4 a4 = reinterpret_cast<const float4*>(a.actions)[i];
-    const float act[4] = {a4.x, a4.y, a4.z, a4.w};
-    const Rng<T, RNG> rng = make_rng<T, RNG>(a, i, a.b.tape_step, a.dump_step);
-    const int n_ep = (int)w[L.ep_length] + 1;             // 1-based step index in the episode
-    T la_prev[4];
+    // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0)
+    for (int s = 0; s < H - 1; ++s) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) la_prev[k] = w[L.last_action + k];
-
-    // ---- physics sub-steps; the observation call after each one is discarded by the
-    // reference (base.py:464) but advances the gyro bias / low-pass state (quirk A.6-1)
-    int slot = 0;
-    for (int s = 0; s < c.agg; ++s) {
-      if constexpr (Mo::BULLET) m.physics_bullet(rng, act, s, slot); else m.physics_simple(rng, act, s, slot);
-      slot += 4;
-      if constexpr (NOISE) {
-        T om[3];
-        m.body_rates(om);
-        const bool full = (s % c.obs_rate) == 0;
-        m.gyro_update(rng, SITE_SUBSTEP + 4 * s + 1, slot + (full ? 12 : 0), om);
-        slot += full ? c.slots_obs_full : c.slots_obs_gyro;
-      }
-    }
-
-    // ---- the observation that is returned (base.py:468 -> compute_history)
-    T target[3] = {c.target[0], c.target[1], c.target[2]};
-    if constexpr (TASK == PDX_TASK_CIRCLE) m.ref_point((n_ep + (int)w[L.ref_offset]) % 300, target);   // circle.py:130
-    if constexpr (TASK == PDX_TASK_TAKEOFF) m.ref_point(min(n_ep * c.agg, 299), target);                // takeoff.py:108
-    T actT[4] = {(T)act[0], (T)act[1], (T)act[2], (T)act[3]};
-    T q_true[4] = {T(0), T(0), T(0), T(1)};
-    if constexpr (!NOISE) {
-      if constexpr (Mo::BULLET) { for (int k = 0; k < 4; ++k) q_true[k] = w[L.quat + k]; }
-      else quat_from_euler(w[L.rpy], w[L.rpy + 1], w[L.rpy + 2], q_true);
-    }
-    T core[C];
-    m.observe(rng, SITE_FINAL_OBS, slot, target, actT, q_true, core);
-
-    // ---- history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319)
-    const int H = c.history;
-    const int g = (int)w[L.hist_phase];
-    obs_row = reinterpret_cast<T*>(a.b.obs) + i * c.obs_dim;
-    // quirk (Bullet agent): after a reset the action deque holds H references to ring[-1]
-    // (agents.py:386, base.py:426-427), which the latency ring overwrites in place with the
-    // current action -> those entries read as the *current* action.
-    const bool latency = Mo::BULLET && c.use_latency;
-    for (int j = 0; j < H - 1; ++j) {
-      const int pos = (g + j) % (H - 1);
-      const bool alias = latency && (j + n_ep <= H);
       for (int qd = 0; qd < QH; ++qd) {
         T v[4];
-        load_quad(state, n, i, L.n_quads + pos * QH + qd, v);
+        load_quad(state, n, i, L.n_quads + s * QH + qd, v);
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int idx = qd * 4 + l;
-          if (idx < E) {
-            T val = v[l];
-            if (alias && idx >= C) val = actT[idx - C];
-            obs_row[j * E + idx] = val;
+        for (int l = 0; l < 4; ++l) if (qd * 4 + l < E) my_row1[(s + 1) * E + qd * 4 + l] = v[l];
+      }
+    }
+  }
+  bool block_any = false;
+  const bool latency = Mo::BULLET && c.use_latency;
+  T* w = m.w;
+
+  for (int t = 0; t < a.n_steps; ++t) {
+    T* tn = (t & 1) ? my_row1 : my_row0;             // this step's row, previous step's row
+    const T* to = (t & 1) ? my_row0 : my_row1;
+    const int64_t tn_off = (int64_t)t * n;           // offset of step t in the [n_steps][n] outputs
+    bool fin = false;
+    T ep_ret_out = T(0);
+    int ep_len_out = 0;
+    T core[C], a_new[4], actT[4];
+    int n_ep = 0;
+
+    if (valid) {
+      const float4 a4 = reinterpret_cast<const float4*>(a.actions)[tn_off + i];
+      const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+      const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter + (uint64_t)t, i,
+                                               a.b.tape_step ? a.b.tape_step + (int64_t)t * c.slots_step * n : nullptr,
+                                               a.dump_step ? a.dump_step + (int64_t)t * c.slots_step * n : nullptr);
+      n_ep = (int)w[L.ep_length] + 1;                // 1-based step index in the episode
+      T la_prev[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { la_prev[k] = w[L.last_action + k]; actT[k] = (T)act[k]; }
+
+      // ---- physics sub-steps; the observation call after each one is discarded by the
+      // reference (base.py:464) but advances the gyro bias / low-pass state (quirk A.6-1)
+      int slot = 0;
+      for (int s = 0; s < c.agg; ++s) {
+        const bool full = (s % c.obs_rate) == 0;
+        m.substep(rng, act, s, slot, full);
+        slot += 4 + (NOISE ? (full ? c.slots_obs_full : c.slots_obs_gyro) : 0);
+      }
+
+      // ---- the observation that is returned (base.py:468 -> compute_history)
+      T target[3] = {c.target[0], c.target[1], c.target[2]};
+      if constexpr (TASK == PDX_TASK_CIRCLE) m.ref_point((n_ep + (int)w[L.ref_offset]) % 300, target);   // circle.py:130
+      if constexpr (TASK == PDX_TASK_TAKEOFF) m.ref_point(min(n_ep * c.agg, 299), target);                // takeoff.py:108
+      T q_true[4] = {T(0), T(0), T(0), T(1)};
+      if constexpr (!NOISE) {
+        if constexpr (Mo::BULLET) { for (int k = 0; k < 4; ++k) q_true[k] = w[L.quat + k]; }
+        else quat_from_euler(w[L.rpy], w[L.rpy + 1], w[L.rpy + 2], q_true);
+      }
+      m.observe(rng, SITE_FINAL_OBS, slot, target, actT, q_true, core);
+
+      // a(k-1) paired with o(k).  quirk (Bullet agent): after a reset the action deque holds H
+      // references to ring[-1] (agents.py:386, base.py:426-427), which the latency ring
+      // overwrites in place with the current action -> those entries read as the *current*
+      // action for as long as they stay in the deque.
+      {
+        const bool alias = latency && (H - 1 + n_ep <= H);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a_new[k] = alias ? actT[k] : la_prev[k];
+      }
+
+      // ---- reward / cost / done
+      T e[3], om[3];
+      m.euler(e);
+      m.body_rates(om);
+      const bool dn = m.done(e, om, target);
+      // action penalties are float32 arithmetic in the reference (float32 action array)
+      float nca2 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = 0.5f * (fminf(fmaxf(act[k], -1.0f), 1.0f) + 1.0f);
+        nca2 += v * v;
+      }
+      const T pa = (T)((float)c.pen_action * sqrtf(nca2));
+      T par = T(0);
+      if constexpr (TASK == PDX_TASK_CIRCLE) {                        // circle.py:186 (hover/takeoff: == 0, A.6-10)
+        T d2 = T(0);
+        if (!(latency && n_ep == 1)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const T d = actT[k] - la_prev[k]; d2 += d * d; }
+        }
+        par = c.arp * M<T>::sqrt(d2);
+      }
+      const T prpy = c.pen_angle * norm3(e[0], e[1], e[2]);
+      const T pspin = c.pen_spin * norm3(om[0], om[1], om[2]);
+      const T pterm = dn ? c.pen_terminal : T(0);
+      const T cvel = TASK == PDX_TASK_TAKEOFF ? c.pen_action : c.pen_velocity;   // takeoff.py:165
+      const T pvel = cvel * norm3(w[L.vel], w[L.vel + 1], w[L.vel + 2]);
+      const T penalties = ((((prpy + par) + pspin) + pvel) + pa) + pterm;
+      const T dist = norm3(w[L.xyz] - target[0], w[L.xyz + 1] - target[1], w[L.xyz + 2] - target[2]);
+      T r = -dist - penalties;
+      if (TASK == PDX_TASK_TAKEOFF && w[L.xyz + 2] < T(0.08)) r -= T(1);
+      const T cst = m.cost(e, om, act);
+
+      // ---- episode accounting, TimeLimit (__init__.py:11)
+      w[L.ep_return] += r;
+      w[L.ep_length] = (T)n_ep;
+      bool trunc = n_ep >= c.max_episode_steps;
+      if (c.reset_on_nonfinite) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ok = ok && M<T>::finite(w[L.xyz + k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ok = ok && M<T>::finite(om[k]) && M<T>::finite(e[k]);
+        trunc = trunc || !ok;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[L.last_action + k] = actT[k];
+      reinterpret_cast<T*>(a.b.reward)[tn_off + i] = r;
+      reinterpret_cast<T*>(a.b.cost)[tn_off + i] = cst;
+      a.b.terminated[tn_off + i] = dn ? 1 : 0;
+      a.b.truncated[tn_off + i] = trunc ? 1 : 0;
+      fin = dn || trunc;
+      ep_ret_out = w[L.ep_return];
+      ep_len_out = n_ep;
+      if (a.b.episode_return) reinterpret_cast<T*>(a.b.episode_return)[tn_off + i] = fin ? ep_ret_out : T(0);
+      if (a.b.episode_length) a.b.episode_length[tn_off + i] = fin ? ep_len_out : 0;
+    }
+
+    // ---- block vote.  This barrier also orders the row writes below after the bulk copy that
+    // last read this tile (thread 0 waited for it right after issuing the previous copy).
+    const int any_fin = __syncthreads_or(fin ? 1 : 0);
+
+    if (valid) {
+      // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319)
+      for (int j = 0; j < H - 1; ++j) {
+        const bool alias = latency && (j + n_ep <= H);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          T v = to[(j + 1) * E + k];
+          if (k >= C && alias) v = actT[k >= C ? k - C : 0];
+          tn[j * E + k] = v;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
+    }
+
+    // ---- auto-reset of finished episodes, compacted over the block
+    if (any_fin) {
+      block_any = true;
+      const bool do_reset = fin && c.auto_reset;
+      const unsigned ballot = __ballot_sync(0xffffffffu, fin);
+      if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+      __syncthreads();
+      int my_rank = __popc(ballot & ((1u << lane) - 1u)), total = 0;
+      for (int wv = 0; wv < (B >> 5); ++wv) {
+        const int cnt = s_warp_cnt[wv];
+        if (wv < warp) my_rank += cnt;
+        total += cnt;
+      }
+      if (do_reset && a.b.final_obs) {                       // last observation of the episode
+        T* fo = reinterpret_cast<T*>(a.b.final_obs) + (tn_off + i) * D;
+        for (int k = 0; k < D; ++k) fo[k] = tn[k];
+      }
+      for (int chunk = 0; chunk < total; chunk += kSlots) {
+        const bool mine = fin && my_rank >= chunk && my_rank < chunk + kSlots;
+        const int sl = my_rank - chunk;
+        if (mine) {                                          // hand-over: what a reset needs
+          T stale[3];
+          m.body_rates(stale);
+          slots[0 * kSlots + sl] = (T)tid;
+          slots[1 * kSlots + sl] = ep_ret_out;
+          slots[2 * kSlots + sl] = (T)ep_len_out;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) slots[(3 + k) * kSlots + sl] = stale[k];
+          if constexpr (NOISE) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) slots[(6 + k) * kSlots + sl] = w[L.gyro_bias + k];
+          }
+          if constexpr (TASK == PDX_TASK_CIRCLE) slots[9 * kSlots + sl] = w[L.ref_offset];
+        }
+        __syncthreads();
+        const int cnt = min(kSlots, total - chunk);
+        if (warp == 0) {
+          double s_cnt = 0.0, s_ret = 0.0, s_ret2 = 0.0, s_len = 0.0;
+          double mn = 1e300, mx = -1e300, ln = 1e300, lx = -1e300;
+          if (lane < cnt) {
+            const int owner = (int)slots[0 * kSlots + lane];
+            const double ret = (double)slots[1 * kSlots + lane], len = (double)slots[2 * kSlots + lane];
+            s_cnt = 1.0; s_ret = ret; s_ret2 = ret * ret; s_len = len;
+            mn = mx = ret; ln = lx = len;
+            if (c.auto_reset) {
+              // park my own environment, become a scratch environment for the owner's reset
+#pragma unroll
+              for (int k = 0; k < NW; ++k) park[k * kSlots + lane] = w[k];
+              T stale[3], o1[C], o2[C];
+#pragma unroll
+              for (int k = 0; k < NW; ++k) w[k] = T(0);
+#pragma unroll
+              for (int k = 0; k < 3; ++k) stale[k] = slots[(3 + k) * kSlots + lane];
+              if constexpr (NOISE) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[L.gyro_bias + k] = slots[(6 + k) * kSlots + lane];
+              }
+              if constexpr (TASK == PDX_TASK_CIRCLE) w[L.ref_offset] = slots[9 * kSlots + lane];
+              // nominal parameters are what a reset without domain randomisation leaves behind
+              w[L.dt] = c.time_step; w[L.mass] = c.mass; w[L.ftf1] = c.ftf1;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) w[L.inertia + k] = c.inertia[k];
+              if constexpr (Mo::BULLET) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { w[L.motor_b + k] = T(1) * c.time_step / c.motor_tc; w[L.motor_k + k] = c.max_thrust; }
+              }
+              const int64_t io = block_base + owner;
+              const Rng<T, RNG> rr = make_rng<T, RNG>(a, a.counter + (uint64_t)t, io,
+                                                      a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
+                                                      a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
+              reset_env(m, rr, stale, o1, o2);
+#pragma unroll
+              for (int k = 0; k < NW; ++k) slots[k * kSlots + lane] = w[k];
+#pragma unroll
+              for (int k = 0; k < C; ++k) { slots[(NW + k) * kSlots + lane] = o1[k]; slots[(NW + C + k) * kSlots + lane] = o2[k]; }
+#pragma unroll
+              for (int k = 0; k < NW; ++k) w[k] = park[k * kSlots + lane];
+            }
+          }
+          if (a.b.episode_stats) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s_cnt += __shfl_xor_sync(0xffffffffu, s_cnt, o);
+              s_ret += __shfl_xor_sync(0xffffffffu, s_ret, o);
+              s_ret2 += __shfl_xor_sync(0xffffffffu, s_ret2, o);
+              s_len += __shfl_xor_sync(0xffffffffu, s_len, o);
+              mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+              mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+              ln = fmin(ln, __shfl_xor_sync(0xffffffffu, ln, o));
+              lx = fmax(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+            }
+            if (lane == 0) {
+              s_stats[0] += s_cnt; s_stats[1] += s_ret; s_stats[2] += s_ret2; s_stats[3] += s_len;
+              s_stats[4] = fmin(s_stats[4], mn); s_stats[5] = fmax(s_stats[5], mx);
+              s_stats[6] = fmin(s_stats[6], ln); s_stats[7] = fmax(s_stats[7], lx);
+            }
           }
         }
-      }
-    }
-    T a_new[4];                                          // a(k-1) paired with o(k)
-    {
-      const bool alias = latency && (H - 1 + n_ep <= H);
+        __syncthreads();
+        if (mine && do_reset) {                              // take the new episode back
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a_new[k] = alias ? actT[k] : la_prev[k];
+          for (int k = 0; k < NW; ++k) {
+            if (!(k >= L.ou && k < L.ou + 4)) w[k] = slots[k * kSlots + sl];   // OU state survives
+          }
+          for (int j = 0; j < H; ++j) {
+            const int src = NW + (j == H - 1 ? C : 0);
 #pragma unroll
-      for (int k = 0; k < C; ++k) obs_row[(H - 1) * E + k] = core[k];
+            for (int k = 0; k < C; ++k) tn[j * E + k] = slots[(src + k) * kSlots + sl];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) obs_row[(H - 1) * E + C + k] = a_new[k];
-    }
-    if (H > 1) {                                         // newest entry replaces the oldest
-      const int pos0 = g % (H - 1);
-#pragma unroll
-      for (int qd = 0; qd < QH; ++qd) {
-        T v[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int idx = qd * 4 + l;
-          v[l] = idx < C ? core[idx < C ? idx : 0] : (idx < E ? la_prev[idx - C < 4 ? idx - C : 0] : T(0));
+            for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
+          }
         }
-        store_quad(state, n, i, L.n_quads + pos0 * QH + qd, v);
+        if (chunk + kSlots < total) __syncthreads();         // slots are reused by the next pass
       }
     }
 
-    // ---- reward / cost / done
-    T e[3], om[3];
-    m.euler(e);
-    m.body_rates(om);
-    const bool dn = m.done(e, om, target);
-    // action penalties are float32 arithmetic in the reference (float32 action array)
-    float nca2 = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float v = 0.5f * (fminf(fmaxf(act[k], -1.0f), 1.0f) + 1.0f);
-      nca2 += v * v;
-    }
-    const T pa = (T)((float)c.pen_action * sqrtf(nca2));
-    T par = T(0);
-    if constexpr (TASK == PDX_TASK_CIRCLE) {                        // circle.py:186 (hover/takeoff: == 0, A.6-10)
-      T d2 = T(0);
-      if (!(latency && n_ep == 1)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const T d = actT[k] - la_prev[k]; d2 += d * d; }
+    // ---- observation rows of the block leave as one bulk copy (or a flat coalesced copy when
+    // the destination does not meet the 16-byte rules of the bulk engine)
+    T* gdst = reinterpret_cast<T*>(a.b.obs) + (tn_off + block_base) * D;
+    const T* tile = (t & 1) ? tile1 : tile0;
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)D * (uint32_t)sizeof(T);
+    const bool bulk = ((reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
+    if (bulk) {
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(gdst, tile, bytes);
+        bulk_wait_read<1>();          // the copy issued one step ago has finished reading its tile
       }
-      par = c.arp * M<T>::sqrt(d2);
+    } else {
+      __syncthreads();
+      for (int e = tid; e < rows * D; e += B) gdst[e] = tile[e];
     }
-    const T prpy = c.pen_angle * norm3(e[0], e[1], e[2]);
-    const T pspin = c.pen_spin * norm3(om[0], om[1], om[2]);
-    const T pterm = dn ? c.pen_terminal : T(0);
-    const T cvel = TASK == PDX_TASK_TAKEOFF ? c.pen_action : c.pen_velocity;   // takeoff.py:165
-    const T pvel = cvel * norm3(w[L.vel], w[L.vel + 1], w[L.vel + 2]);
-    const T penalties = ((((prpy + par) + pspin) + pvel) + pa) + pterm;
-    const T dist = norm3(w[L.xyz] - target[0], w[L.xyz + 1] - target[1], w[L.xyz + 2] - target[2]);
-    T r = -dist - penalties;
-    if (TASK == PDX_TASK_TAKEOFF && w[L.xyz + 2] < T(0.08)) r -= T(1);
-    const T cst = m.cost(e, om, act);
-
-    // ---- episode accounting, TimeLimit (__init__.py:11)
-    w[L.ep_return] += r;
-    w[L.ep_length] = (T)n_ep;
-    w[L.hist_phase] = (T)((g + 1) % (H > 1 ? 4 * (H - 1) : 1));
-    bool trunc = n_ep >= c.max_episode_steps;
-    if (c.reset_on_nonfinite) {
-      bool ok = true;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) ok = ok && M<T>::finite(w[L.xyz + k]);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) ok = ok && M<T>::finite(om[k]) && M<T>::finite(e[k]);
-      trunc = trunc || !ok;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[L.last_action + k] = actT[k];
-    reinterpret_cast<T*>(a.b.reward)[i] = r;
-    reinterpret_cast<T*>(a.b.cost)[i] = cst;
-    a.b.terminated[i] = dn ? 1 : 0;
-    a.b.truncated[i] = trunc ? 1 : 0;
-    fin = dn || trunc;
-    ep_ret_out = w[L.ep_return];
-    ep_len_out = n_ep;
-    if (a.b.episode_return) reinterpret_cast<T*>(a.b.episode_return)[i] = fin ? ep_ret_out : T(0);
-    if (a.b.episode_length) a.b.episode_length[i] = fin ? ep_len_out : 0;
   }
 
-  // ---- per-block episode statistics: warp shuffles, then one set of atomics per block
-  if (a.b.episode_stats) {
-    const unsigned any = __ballot_sync(0xffffffffu, fin);
-    if (any) {
-      double cnt = fin ? 1.0 : 0.0, sr = fin ? (double)ep_ret_out : 0.0, sl = fin ? (double)ep_len_out : 0.0;
-      double sr2 = sr * sr;
-      double mn = fin ? (double)ep_ret_out : 1e300, mx = fin ? (double)ep_ret_out : -1e300;
-      double ln = fin ? (double)ep_len_out : 1e300, lx = fin ? (double)ep_len_out : -1e300;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        sr2 += __shfl_xor_sync(0xffffffffu, sr2, o);
-        sl += __shfl_xor_sync(0xffffffffu, sl, o);
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        ln = fmin(ln, __shfl_xor_sync(0xffffffffu, ln, o));
-        lx = fmax(lx, __shfl_xor_sync(0xffffffffu, lx, o));
-      }
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_stats[0], cnt); atomicAdd(&s_stats[1], sr); atomicAdd(&s_stats[2], sr2);
-        atomicAdd(&s_stats[3], sl);
-        atomic_min_double(&s_stats[4], mn); atomic_max_double(&s_stats[5], mx);
-        atomic_min_double(&s_stats[6], ln); atomic_max_double(&s_stats[7], lx);
-        s_any = 1;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_any) {
+  // ---- epilogue: state and history back to HBM, statistics, drain the bulk engine
+  if (valid) {
+    m.store(state, n, i, true);
+    const T* last = ((a.n_steps - 1) & 1) ? my_row1 : my_row0;
+    store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) { return last[(s + 1) * E + idx]; });
+  }
+  if (tid == 0) {
+    if (block_any && a.b.episode_stats) {
       double* gs = a.b.episode_stats;
       atomicAdd(&gs[0], s_stats[0]); atomicAdd(&gs[1], s_stats[1]); atomicAdd(&gs[2], s_stats[2]);
       atomicAdd(&gs[3], s_stats[3]);
       atomic_min_double(&gs[4], s_stats[4]); atomic_max_double(&gs[5], s_stats[5]);
       atomic_min_double(&gs[6], s_stats[6]); atomic_max_double(&gs[7], s_stats[7]);
     }
-  }
-
-  if (valid) {
-    const bool do_reset = fin && c.auto_reset;
-    if (do_reset) {                                      // auto-reset in the same launch
-      if (a.b.final_obs) {
-        T* fo = reinterpret_cast<T*>(a.b.final_obs) + i * c.obs_dim;
-        for (int k = 0; k < c.obs_dim; ++k) fo[k] = obs_row[k];
-      }
-      const Rng<T, RNG> rr = make_rng<T, RNG>(a, i, a.b.tape_reset, a.dump_reset);
-      reset_env(m, rr, state, n, i, obs_row);
-    }
-    m.store(state, n, i, do_reset);
+    bulk_wait_all();
   }
 }
 

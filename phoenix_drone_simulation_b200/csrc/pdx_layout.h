@@ -18,14 +18,16 @@ struct Layout {
   int dt, mass, inertia, ftf1;
   int motor_b, motor_k, motor_x, ring, ring_idx;   // Bullet agent only
   int ou, last_action;
-  int ep_return, ep_length, hist_phase;
+  int ep_return, ep_length;
   int ref_offset;          // circle only
   int gyro_bias, gyro_lpf; // noise only
   int n_words;             // words before the history ring
   int n_dyn_words;         // words that a non-resetting step writes back
   int n_store_quads;       // quads that hold at least one per-step word
   int n_quads;             // ceil(n_words / 4)
-  int hist_quads;          // quads per history slot: ceil((C + 4) / 4)
+  int hist_quads;          // quads per history slot: ceil((C + 4) / 4).  The H-1 slots follow the
+                           // n_quads state quads; slot s holds entry s+1 of the last emitted
+                           // observation row (= entry s of the next one), base.py:303-319
   int core_dim;            // C
 };
 
@@ -59,7 +61,6 @@ constexpr Layout make_layout(int task, int physics, bool noise) {
   L.last_action = take(4);
   L.ep_return = take(1);
   L.ep_length = take(1);
-  L.hist_phase = take(1);
   L.gyro_bias = L.gyro_lpf = -1;
   if (noise) {
     L.gyro_bias = take(3);

@@ -21,19 +21,23 @@ template <> struct M<float> {
   static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
   static __device__ __forceinline__ float floor(float x) { return floorf(x); }
   static __device__ __forceinline__ bool finite(float x) { return isfinite(x); }
-  // Box-Muller on two 32-bit words: fast intrinsics (MUFU lg2/sin/cos) -- noise quality,
-  // not trajectory accuracy, is what matters here.
+  // Box-Muller on two 32-bit words.  Throughput path: uniforms are built with bit operations
+  // (no I2F on the XU pipe), log2 / sqrt / sin / cos are single MUFU operations -- noise
+  // quality, not trajectory accuracy, is what matters here.
   static __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
-    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
-    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * __logf(u1));
-    float s, c;
-    __sincosf(6.283185307179586f * u2, &s, &c);
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));     // (0,1]
+    const float u2 = __uint_as_float(0x3f800000u | (b >> 9)) - 1.0f;     // [0,1)
+    float l2, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // -2 ln u1
+    const float ang = 6.283185307179586f * u2;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
     *z0 = r * c;
     *z1 = r * s;
   }
   static __device__ __forceinline__ float unit(uint32_t a) {             // [0,1)
-    return (float)(a >> 8) * (1.0f / 16777216.0f);
+    return __uint_as_float(0x3f800000u | (a >> 9)) - 1.0f;
   }
 };
 
@@ -122,16 +126,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// Draw-site ids (4th counter word).  One Philox call per site yields up to 4 variates.
+// Draw-site ids (4th counter word).  One Philox call per site id yields 4 words; a draw block
+// of K variates occupies ceil(K/4) consecutive ids.
 enum DrawSite : uint32_t {
-  SITE_SUBSTEP = 0,      // + 4*substep : +0 OU(4n)  +1 gyro bias(3n)  +2 random walk(3n)  +3 turn-on(3n)
-  SITE_FINAL_OBS = 40,   // + 0..7 : pos n, pos u, vel n, bias, rw, turn-on, theta n, theta u
-  SITE_RESET = 64,       // +0 pos u(3)+yaw, +1 rpy u(3)+yaw rate, +2 vel u(3), +3 rates u(3)/ref offset,
-                         // +4 motor x n(4), +5/+6 ring rows n(4)
-  SITE_DR = 72,          // +0 dt,m,Jx,Jy  +1 Jz,ftf0,ftf1  +2 motor T(4)  +3 T2W(4)
-  SITE_RESET_OBS1 = 76,  // + 0..7
-  SITE_RESET_OBS2 = 84,  // + 0..7
-  SITE_INIT = 96,        // constructor observation call: gyro bias (3n)
+  SITE_SUBSTEP = 0,      // + 8*substep : +0..3  OU(4n) + gyro bias / random walk / turn-on (9n)
+  SITE_FINAL_OBS = 64,   // +0..4 normals: pos(3) vel(3) gyro(9) theta(3); +5,+6 uniforms: pos(3) theta(3)
+  SITE_RESET = 80,       // +0..3 task uniforms (<=14), +4..6 motor x / ring rows normals (4+8)
+  SITE_DR = 88,          // +0..3 dt,m,Jx,Jy,Jz,ftf0,ftf1, motor T(4), T2W(4) uniforms
+  SITE_RESET_OBS1 = 96,  // like SITE_FINAL_OBS
+  SITE_RESET_OBS2 = 104,
+  SITE_INIT = 112,       // constructor observation call: gyro bias (3n)
 };
 
 // Per-thread RNG context.
@@ -151,53 +155,74 @@ struct Rng {
   __device__ __forceinline__ uint4 raw(uint32_t site) const {
     return philox4x32_10(make_uint4(env_lo, ctr_lo, env_hi, site), key);
   }
+  // K standard normals / unit uniforms from ceil(K/4) consecutive draw sites starting at
+  // `site0` (Box-Muller pairs words (2j, 2j+1) of the concatenated raw stream).
   template <int K>
-  __device__ __forceinline__ void philox_normals(uint32_t site, T* out) const {
-    const uint4 r = raw(site);
-    T z[4];
-    M<T>::box_muller(r.x, r.y, &z[0], &z[1]);
-    if (K > 2) M<T>::box_muller(r.z, r.w, &z[2], &z[3]);
+  __device__ __forceinline__ void philox_normals(uint32_t site0, T* out) const {
 #pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = z[k];
-  }
-  template <int K>
-  __device__ __forceinline__ void philox_uniforms(uint32_t site, T* out) const {
-    const uint4 r = raw(site);
-    const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+    for (int c = 0; c < (K + 3) / 4; ++c) {
+      const uint4 r = raw(site0 + c);
+      T z[4];
+      M<T>::box_muller(r.x, r.y, &z[0], &z[1]);
+      if (4 * c + 2 < K) M<T>::box_muller(r.z, r.w, &z[2], &z[3]);
 #pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = M<T>::unit(v[k]);
-  }
-  // K standard normals from draw site `site` (tape: slots slot..slot+K-1).
-  template <int K>
-  __device__ __forceinline__ void normals(uint32_t site, int slot, T* out) const {
-    if (MODE == PDX_RNG_TAPE) {
-      if (dump) {
-        philox_normals<K>(site, out);
-#pragma unroll
-        for (int k = 0; k < K; ++k) dump[(int64_t)(slot + k) * stride] = (double)out[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) out[k] = (T)tape[(int64_t)(slot + k) * stride];
-      }
-    } else {
-      philox_normals<K>(site, out);
+      for (int k = 0; k < 4; ++k) if (4 * c + k < K) out[4 * c + k] = z[k];
     }
   }
-  // K uniforms in [0,1).
   template <int K>
-  __device__ __forceinline__ void uniforms(uint32_t site, int slot, T* out) const {
+  __device__ __forceinline__ void philox_uniforms(uint32_t site0, T* out) const {
+#pragma unroll
+    for (int c = 0; c < (K + 3) / 4; ++c) {
+      const uint4 r = raw(site0 + c);
+      const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (4 * c + k < K) out[4 * c + k] = M<T>::unit(v[k]);
+    }
+  }
+  // Tape slot of draw k: slot0 + k, or slot0 + rel[k] when the reference interleaves other draws.
+  template <int K>
+  __device__ __forceinline__ void normals_at(uint32_t site0, int slot0, const int (&rel)[K], T* out) const {
     if (MODE == PDX_RNG_TAPE) {
       if (dump) {
-        philox_uniforms<K>(site, out);
+        philox_normals<K>(site0, out);
 #pragma unroll
-        for (int k = 0; k < K; ++k) dump[(int64_t)(slot + k) * stride] = (double)out[k];
+        for (int k = 0; k < K; ++k) dump[(int64_t)(slot0 + rel[k]) * stride] = (double)out[k];
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) out[k] = (T)tape[(int64_t)(slot + k) * stride];
+        for (int k = 0; k < K; ++k) out[k] = (T)tape[(int64_t)(slot0 + rel[k]) * stride];
       }
     } else {
-      philox_uniforms<K>(site, out);
+      philox_normals<K>(site0, out);
     }
+  }
+  template <int K>
+  __device__ __forceinline__ void uniforms_at(uint32_t site0, int slot0, const int (&rel)[K], T* out) const {
+    if (MODE == PDX_RNG_TAPE) {
+      if (dump) {
+        philox_uniforms<K>(site0, out);
+#pragma unroll
+        for (int k = 0; k < K; ++k) dump[(int64_t)(slot0 + rel[k]) * stride] = (double)out[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = (T)tape[(int64_t)(slot0 + rel[k]) * stride];
+      }
+    } else {
+      philox_uniforms<K>(site0, out);
+    }
+  }
+  template <int K>
+  __device__ __forceinline__ void normals(uint32_t site0, int slot0, T* out) const {
+    int rel[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rel[k] = k;
+    normals_at<K>(site0, slot0, rel, out);
+  }
+  template <int K>
+  __device__ __forceinline__ void uniforms(uint32_t site0, int slot0, T* out) const {
+    int rel[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rel[k] = k;
+    uniforms_at<K>(site0, slot0, rel, out);
   }
 };
 

@@ -26,7 +26,7 @@ template <class T>
 struct DevCfg {
   int history, agg, obs_rate, use_latency, buf_size, use_motor_dynamics, reset_distribution,
       ground_effect, max_episode_steps, core_dim, obs_dim, dr_on, reset_on_nonfinite, auto_reset;
-  int slots_obs_full, slots_obs_gyro, slots_reset_task, slots_reset_dr;
+  int slots_obs_full, slots_obs_gyro, slots_reset_task, slots_reset_dr, slots_step, slots_reset;
   T dr, time_step, mass, inertia[3], arm, gravity, thrust2weight, max_thrust,
       k_mass_dr, ftf1, hover_x, hover_action, motor_tc, ou_theta, ou_sigma, lpf_ratio,
       pos_std, pos_unif, vel_std, quat_std, quat_unif, gyro_pi, gyro_sigma_b, gyro_rw, gyro_to,
@@ -68,17 +68,6 @@ template <class T> __device__ __forceinline__ T clampT(T x, T lo, T hi) {
 template <class T> __device__ __forceinline__ T norm3(T a, T b, T c) {
   return M<T>::sqrt(a * a + b * b + c * c);
 }
-
-// Row writer for the observation of one env ([n_envs][obs_dim], row-major).
-template <class T>
-struct ObsRow {
-  T* row;
-  T* row2;   // optional second destination (final_obs), may be null
-  __device__ __forceinline__ void put(int idx, T v) const {
-    row[idx] = v;
-    if (row2) row2[idx] = v;
-  }
-};
 
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
 struct Model {
@@ -141,8 +130,7 @@ struct Model {
   // ------------------------------------------------------------------------------------------
   //  motor model -> forces[4], z torque.   `substep` picks the OU draw site / tape slot.
   // ------------------------------------------------------------------------------------------
-  __device__ __forceinline__ void motor(const Rng<T, RNG>& rng, const float a[4], int substep,
-                                        int slot, T f[4], T* tz) {
+  __device__ __forceinline__ void motor(const T z[4], const float a[4], T f[4], T* tz) {
     T u[4];
     bool delayed = false;
     if constexpr (BULLET) {
@@ -169,8 +157,6 @@ struct Model {
         u[k] = (T)(pwm / 60000.0f);
       }
     }
-    T z[4];
-    rng.template normals<4>(SITE_SUBSTEP + 4 * substep, slot, z);
     T tq[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -208,10 +194,9 @@ struct Model {
     }
   }
 
-  __device__ __forceinline__ void physics_simple(const Rng<T, RNG>& rng, const float a[4],
-                                                 int substep, int slot) {
+  __device__ __forceinline__ void physics_simple(const T z_ou[4], const float a[4]) {
     T f[4], tz;
-    motor(rng, a, substep, slot, f, &tz);
+    motor(z_ou, a, f, &tz);
     T q[4], R[9];
     quat_from_euler(w[L.rpy], w[L.rpy + 1], w[L.rpy + 2], q);
     rot_from_quat(q, R);
@@ -239,10 +224,9 @@ struct Model {
     p[2] = M<T>::fmax(p[2], T(0));             // physics.py:182
   }
 
-  __device__ __forceinline__ void physics_bullet(const Rng<T, RNG>& rng, const float a[4],
-                                                 int substep, int slot) {
+  __device__ __forceinline__ void physics_bullet(const T z_ou[4], const float a[4]) {
     T f[4], tz;
-    motor(rng, a, substep, slot, f, &tz);
+    motor(z_ou, a, f, &tz);
     T R[9];
     rot_from_quat(&w[L.quat], R);
     T* v = &w[L.vel];
@@ -317,25 +301,41 @@ struct Model {
   //  observation
   // ------------------------------------------------------------------------------------------
   // sensors.py:121-134 + envs/utils.py:76-79: gyro bias random walk, white noise, low pass.
-  __device__ __forceinline__ void gyro_update(const Rng<T, RNG>& rng, uint32_t site, int slot,
-                                              const T om[3]) {
-    T n1[3], n2[3], n3[3];
-    rng.template normals<3>(site, slot, n1);
-    rng.template normals<3>(site + 1, slot + 3, n2);
-    rng.template normals<3>(site + 2, slot + 6, n3);
+  // n[0..2] bias, n[3..5] random walk, n[6..8] turn-on draws.
+  __device__ __forceinline__ void gyro_update(const T n[9], const T om[3]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       T& b = w[L.gyro_bias + k];
-      b = c.gyro_pi * b + c.gyro_sigma_b * n1[k];
-      const T noisy = ((om[k] + b) + c.gyro_rw * n2[k]) + c.gyro_to * n3[k];
+      b = c.gyro_pi * b + c.gyro_sigma_b * n[k];
+      const T noisy = ((om[k] + b) + c.gyro_rw * n[3 + k]) + c.gyro_to * n[6 + k];
       T& lp = w[L.gyro_lpf + k];
       lp = (T(1) - c.lpf_ratio) * lp + (T(1) * c.lpf_ratio) * noisy;
     }
   }
 
-  // One full compute_observation() -> core[C].  `site`/`slot`: first draw site / tape slot.
+  // One physics sub-step plus the (discarded) observation call that follows it in the reference
+  // (base.py:461-464): the OU draw and the gyro draws of that call come from one draw block.
+  // `slot`: first tape slot of the sub-step; `full`: the observation call is a full one.
+  __device__ __forceinline__ void substep(const Rng<T, RNG>& rng, const float a[4], int s, int slot, bool full) {
+    if constexpr (NOISE) {
+      const int g0 = 4 + (full ? 12 : 0);
+      const int rel[13] = {0, 1, 2, 3, g0, g0 + 1, g0 + 2, g0 + 3, g0 + 4, g0 + 5, g0 + 6, g0 + 7, g0 + 8};
+      T z[13];
+      rng.template normals_at<13>(SITE_SUBSTEP + 8 * s, slot, rel, z);
+      if constexpr (BULLET) physics_bullet(z, a); else physics_simple(z, a);
+      T om[3];
+      body_rates(om);
+      gyro_update(&z[4], om);
+    } else {
+      T z[4];
+      rng.template normals<4>(SITE_SUBSTEP + 8 * s, slot, z);
+      if constexpr (BULLET) physics_bullet(z, a); else physics_simple(z, a);
+    }
+  }
+
+  // One full compute_observation() -> core[C].  `site0`/`slot`: first draw site / tape slot.
   // `q_true`: quaternion to report when noise is off (drone.quaternion).
-  __device__ __forceinline__ void observe(const Rng<T, RNG>& rng, uint32_t site, int slot,
+  __device__ __forceinline__ void observe(const Rng<T, RNG>& rng, uint32_t site0, int slot,
                                           const T target[3], const T act[4], const T q_true[4],
                                           T core[C]) {
     const T* p = &w[L.xyz];
@@ -344,21 +344,22 @@ struct Model {
     body_rates(om);
     T px[3];
     if constexpr (NOISE) {
-      T pn[3], pu[3], vn[3], tn[3], tu[3], e[3], q[4];
-      rng.template normals<3>(site + 0, slot + 0, pn);
-      rng.template uniforms<3>(site + 1, slot + 3, pu);
-      rng.template normals<3>(site + 2, slot + 6, vn);          // slots 9..11: U(-0,0), unused
-      gyro_update(rng, site + 3, slot + 12, om);
-      rng.template normals<3>(site + 6, slot + 21, tn);
-      rng.template uniforms<3>(site + 7, slot + 24, tu);        // slots 27..32: accelerometer
+      // tape slots of one call (sensors.py:84-118): 0-2 pos n, 3-5 pos u, 6-8 vel n, 9-11 vel u
+      // (zero range, unused), 12-20 gyro n, 21-23 theta n, 24-26 theta u, 27-32 accelerometer.
+      const int reln[18] = {0, 1, 2, 6, 7, 8, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
+      const int relu[6] = {3, 4, 5, 24, 25, 26};
+      T zn[18], zu[6], e[3], q[4];
+      rng.template normals_at<18>(site0, slot, reln, zn);
+      rng.template uniforms_at<6>(site0 + 5, slot, relu, zu);
+      gyro_update(&zn[6], om);
       euler(e);
       const T pi = T(3.14159265358979323846);
       const T lo[3] = {-pi, -pi / T(2), -pi}, hi[3] = {pi, pi / T(2), pi};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        px[k] = p[k] + (c.pos_std * pn[k] + (-c.pos_unif + (c.pos_unif - (-c.pos_unif)) * pu[k]));
-        core[7 + k] = v[k] + c.vel_std * vn[k];
-        const T th = c.quat_std * tn[k] + (-c.quat_unif + (c.quat_unif - (-c.quat_unif)) * tu[k]);
+        px[k] = p[k] + (c.pos_std * zn[k] + (-c.pos_unif + (c.pos_unif - (-c.pos_unif)) * zu[k]));
+        core[7 + k] = v[k] + c.vel_std * zn[3 + k];
+        const T th = c.quat_std * zn[15 + k] + (-c.quat_unif + (c.quat_unif - (-c.quat_unif)) * zu[3 + k]);
         e[k] = clampT(e[k] + th, lo[k], hi[k]);
         core[10 + k] = w[L.gyro_lpf + k];
       }

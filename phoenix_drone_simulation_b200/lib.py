@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 PDX_TASK = {'hover': 0, 'circle': 1, 'takeoff': 2}
 PDX_PHYSICS = {'SimplePhysics': 0, 'PyBulletPhysics': 1}
@@ -84,10 +84,13 @@ def load():
     lib.pdx_tape_slots.argtypes = [P(PdxConfig), P(C.c_int), P(C.c_int), P(C.c_int)]
     lib.pdx_step_bytes.argtypes = [P(PdxConfig)]
     lib.pdx_step_bytes.restype = C.c_int64
+    lib.pdx_rollout_bytes.argtypes = [P(PdxConfig), C.c_int32]
+    lib.pdx_rollout_bytes.restype = C.c_int64
     lib.pdx_device_count.restype = C.c_int
     lib.pdx_init.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_uint64, C.c_uint64, C.c_void_p]
     lib.pdx_reset.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.pdx_step.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.pdx_step_many.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.pdx_dump_draws.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_void_p, C.c_uint64, C.c_uint64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_gae.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -110,6 +113,7 @@ def check(rc):
 EXPORTED_SYMBOLS = [
     'pdx_abi_version', 'pdx_last_error', 'pdx_config_size', 'pdx_buffers_size',
     'pdx_config_finalize', 'pdx_state_quads', 'pdx_state_field', 'pdx_tape_slots',
-    'pdx_step_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step', 'pdx_dump_draws',
+    'pdx_step_bytes', 'pdx_rollout_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step',
+    'pdx_step_many', 'pdx_dump_draws',
     'pdx_gae', 'pdx_moments',
 ]

@@ -163,6 +163,32 @@ class VecEnv:
             info['final_observation'] = self.final_obs
         return self.obs, self.reward, self.terminated, self.truncated, info
 
+    def step_many(self, actions, out):
+        """T env.steps of every environment in ONE kernel launch (state stays in registers
+        between steps; open-loop action sequence).  actions: float32 CUDA tensor [T, N, 4];
+        `out`: dict of time-major CUDA tensors -- 'obs' [T, N, D], 'reward', 'cost' [T, N] (engine
+        dtype), 'terminated', 'truncated' [T, N] (uint8); optional 'final_obs' [T, N, D],
+        'episode_return' [T, N], 'episode_length' [T, N] (int32).  Returns `out`."""
+        assert actions.dtype == torch.float32 and actions.is_contiguous() and actions.device == self.device
+        T = actions.shape[0]
+        assert actions.shape == (T, self.num_envs, 4)
+        buf = _lib.PdxBuffers.from_buffer_copy(self._buf)
+        buf.final_obs = buf.episode_return = buf.episode_length = None
+        for k in ('obs', 'reward', 'cost', 'terminated', 'truncated'):
+            assert k in out, k
+        for k, t in out.items():
+            assert t.is_cuda and t.is_contiguous() and t.shape[0] == T and t.shape[1] == self.num_envs, k
+            setattr(buf, k, t.data_ptr())
+        assert self.rng == 'philox', 'step_many draws on device'
+        _lib.check(self.lib.pdx_step_many(C.byref(self.pdx), C.byref(buf), C.c_void_p(actions.data_ptr()), T,
+                                          self.seed, self._counter + 1, self._stream()))
+        self._counter += T
+        return out
+
+    def rollout_bytes(self, n_steps):
+        """Algorithmic HBM bytes per environment of one n_steps launch (pdx_rollout_bytes)."""
+        return int(self.lib.pdx_rollout_bytes(C.byref(self.pdx), int(n_steps)))
+
     # ---- validation: production Philox draws copied out in tape layout ------------------------
     def dump_init(self):
         t = torch.zeros((max(self.tape_slots['init'], 1), self.num_envs), dtype=torch.float64, device=self.device)

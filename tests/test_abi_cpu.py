@@ -74,19 +74,22 @@ def test_state_layout(lib):
     fw, nw = C.c_int(), C.c_int()
     seen = set()
     for name in ('xyz', 'vel', 'rpy', 'omega', 'ou', 'last_action', 'ep_return', 'ep_length',
-                 'hist_phase', 'gyro_bias', 'gyro_lpf', 'dt', 'mass', 'inertia', 'ftf1'):
+                 'gyro_bias', 'gyro_lpf', 'dt', 'mass', 'inertia', 'ftf1'):
         assert lib.pdx_state_field(C.byref(c), name.encode(), C.byref(fw), C.byref(nw)) == 0
         words = set(range(fw.value, fw.value + nw.value))
         assert not (words & seen), name
         seen |= words
-    assert len(seen) == 35                      # 29 per-step words + 6 per-episode constants
+    assert len(seen) == 34                      # 28 per-step words + 6 per-episode constants
     assert lib.pdx_state_field(C.byref(c), b'hist', C.byref(fw), C.byref(nw)) == 0
     assert fw.value == 36 and nw.value == 20    # one history slot: 13 + 4 words in 5 quads
     assert lib.pdx_state_quads(C.byref(c)) == 14
     assert lib.pdx_state_field(C.byref(c), b'quat', C.byref(fw), C.byref(nw)) != 0     # Bullet only
     assert b'does not exist' in lib.pdx_last_error()
-    # algorithmic bytes per env-step: 52 words read, 46 written, obs 34, r, cost
-    assert lib.pdx_step_bytes(C.byref(c)) == (52 + 46 + 34 + 2) * 4 + 16 + 2
+    # algorithmic bytes per env: state 34 + history 17 words read and written once
+    # per launch; per step obs 34 + reward + cost words, 16 B action, 2 flag bytes
+    assert lib.pdx_step_bytes(C.byref(c)) == (51 + 51 + 34 + 2) * 4 + 16 + 2
+    lib.pdx_rollout_bytes.restype = C.c_int64
+    assert lib.pdx_rollout_bytes(C.byref(c), 64) == (51 + 51) * 4 + 64 * ((34 + 2) * 4 + 16 + 2)
 
 
 def test_unsupported_configurations_are_rejected(lib):

@@ -330,3 +330,36 @@ def test_single_env_dropin_api():
         assert 1 <= steps <= 500
         assert env._max_episode_steps == 500
         env.close()
+
+
+@pytest.mark.parametrize('env_id,kw', [('DroneHoverSimpleEnv-v0', {}), ('DroneCircleBulletEnv-v0', {}),
+                                       ('DroneCircleSimpleEnv-v0', {'observation_history_size': 8}),
+                                       ('DroneTakeOffSimpleEnv-v0', {'max_episode_steps': 7})])
+def test_step_many_equals_repeated_step(env_id, kw):
+    """One fused n_steps launch (state in registers across steps, bulk-copied observation tiles,
+    block-compacted resets) is bit-identical to n_steps single-step launches."""
+    N, T = 1000, 23                      # ragged last block, odd sizes
+    for dtype in (torch.float32, torch.float64):
+        a = _vec(env_id, N, seed=9, dtype=dtype, keep_final_obs=True, **kw)
+        b = _vec(env_id, N, seed=9, dtype=dtype, **kw)
+        assert torch.equal(a.reset(), b.reset())
+        g = torch.Generator(device='cuda').manual_seed(3)
+        acts = (a.cfg.hover_action + 0.5 * torch.randn((T, N, 4), device='cuda', generator=g)).contiguous()
+        out = {'obs': torch.zeros((T, N, a.obs_dim), dtype=dtype, device='cuda'),
+               'reward': torch.zeros((T, N), dtype=dtype, device='cuda'),
+               'cost': torch.zeros((T, N), dtype=dtype, device='cuda'),
+               'terminated': torch.zeros((T, N), dtype=torch.uint8, device='cuda'),
+               'truncated': torch.zeros((T, N), dtype=torch.uint8, device='cuda'),
+               'episode_length': torch.zeros((T, N), dtype=torch.int32, device='cuda')}
+        b.step_many(acts, out)
+        n_fin = 0
+        for t in range(T):
+            o, r, te, tr, info = a.step(acts[t])
+            assert torch.equal(o, out['obs'][t]), (t, dtype)
+            assert torch.equal(r, out['reward'][t]) and torch.equal(info['cost'], out['cost'][t])
+            assert torch.equal(te, out['terminated'][t].bool()) and torch.equal(tr, out['truncated'][t].bool())
+            assert torch.equal(info['episode_length'], out['episode_length'][t])
+            n_fin += int((te | tr).sum())
+        assert torch.equal(a.state, b.state)
+        assert torch.equal(a.episode_stats()[:4], b.episode_stats()[:4]) or torch.allclose(a.episode_stats(), b.episode_stats())
+        assert int(a.episode_stats()[0]) == n_fin and n_fin > 0
