@@ -163,7 +163,7 @@ def workload_config(a, n_per_gpu):
     return {'workload': f'{a.env_id}, {n_per_gpu} lock-step envs per GPU, DR 0.10, observation noise on, '
                         f'H=2, U(-1,1) actions, auto-reset (BASELINE.json configs[1])',
             'env_id': a.env_id, 'envs_per_gpu': n_per_gpu, 'env_steps_per_bench_step': a.inner * n_per_gpu,
-            'inner_env_steps': a.inner, 'rng': 'philox4x32-10 on device',
+            'inner_env_steps': a.inner, 'launch': a.mode, 'rng': 'philox4x32-10 on device',
             'l2': 'actions and observations stream through ring buffers larger than L2; the per-env state '
                   'is L2-resident at this size by the workload definition (see roofline_hbm_resident_off)'}
 
@@ -172,25 +172,30 @@ def workload_config(a, n_per_gpu):
 #  GPU arm
 # =============================================================================================
 class Segment:
-    """One rollout segment: `inner` env.steps into [inner, N, .] tensors of a ring of segments."""
+    """One rollout segment: `inner` env.steps into [inner, N, .] tensors of a ring of segments.
+    mode 'fused': one pdx_step_many launch per segment; 'per-step': `inner` pdx_step launches."""
 
-    def __init__(self, env, inner, n_ring, gen):
+    def __init__(self, env, inner, n_ring, gen, mode='fused'):
         import torch
         n, d, dev = env.num_envs, env.obs_dim, env.device
-        self.env, self.inner, self.n_ring = env, inner, n_ring
+        self.env, self.inner, self.n_ring, self.mode = env, inner, n_ring, mode
         self.actions = torch.rand((n_ring, inner, n, 4), device=dev, generator=gen) * 2 - 1
         self.obs = torch.empty((n_ring, inner, n, d), dtype=env.dtype, device=dev)
         self.reward = torch.empty((n_ring, inner, n), dtype=env.dtype, device=dev)
         self.cost = torch.empty((n_ring, inner, n), dtype=env.dtype, device=dev)
         self.terminated = torch.empty((n_ring, inner, n), dtype=torch.uint8, device=dev)
         self.truncated = torch.empty((n_ring, inner, n), dtype=torch.uint8, device=dev)
-        self.outs = [[{'obs': self.obs[r, t], 'reward': self.reward[r, t], 'cost': self.cost[r, t],
-                       'terminated': self.terminated[r, t], 'truncated': self.truncated[r, t]}
-                      for t in range(inner)] for r in range(n_ring)]
+        self.seg_outs = [{'obs': self.obs[r], 'reward': self.reward[r], 'cost': self.cost[r],
+                          'terminated': self.terminated[r], 'truncated': self.truncated[r]} for r in range(n_ring)]
+        self.outs = [[{k: v[t] for k, v in self.seg_outs[r].items()} for t in range(inner)] for r in range(n_ring)]
 
     def run(self, k):
         r = k % self.n_ring
-        env, acts, outs = self.env, self.actions[r], self.outs[r]
+        env = self.env
+        if self.mode == 'fused':
+            env.step_many(self.actions[r], self.seg_outs[r])
+            return 1
+        acts, outs = self.actions[r], self.outs[r]
         for t in range(self.inner):
             env.step(acts[t], out=outs[t])
         return self.inner
@@ -334,7 +339,7 @@ def run_gpu_arm(a):
     env.reset()
     gen = torch.Generator(device=dev).manual_seed(1234 + ctx.rank)
     seg_bytes = a.inner * n * (16 + env.obs_dim * 4)
-    seg = Segment(env, a.inner, ring_slots(seg_bytes), gen)
+    seg = Segment(env, a.inner, ring_slots(seg_bytes), gen, a.mode)
 
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
@@ -345,12 +350,14 @@ def run_gpu_arm(a):
 
     # roofline of the dominant kernel (the fused step): algorithmic bytes per launch / mean duration
     peak, peak_src = measured_peak()
-    bytes_per_launch = env.step_bytes * n
+    steps_per_launch = a.steps * a.inner // launches
+    bytes_per_launch = env.rollout_bytes(steps_per_launch) * n
     us_per_launch = ms * 1e3 / launches
     achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'pdx::k_step<float, hover, simple, noise, philox>',
-                'bytes_per_env_step': env.step_bytes, 'us_per_launch': us_per_launch, 'peak_source': peak_src}
+                'traffic': None, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
+                'env_steps_per_launch': steps_per_launch * n, 'bytes_per_env_step': bytes_per_launch / (steps_per_launch * n),
+                'us_per_launch': us_per_launch, 'peak_source': peak_src}
 
     e2e_ms, h2d, d2h = time_e2e(env, a.inner, max(1, a.steps // a.e2e_div), a.warmup, ctx, 99 + ctx.rank)
     e2e_steps = max(1, a.steps // a.e2e_div) * a.inner * n * ctx.world
@@ -363,14 +370,17 @@ def run_gpu_arm(a):
         nl = a.large_envs
         big = VecEnv(a.env_id, nl, device=dev, dtype=torch.float32, seed=a.seed + 1)
         big.reset()
-        inner_l = 4
-        segl = Segment(big, inner_l, 2, gen)
-        msl, ll = time_device(big, segl, max(4, a.steps // 8), 3, ctx)
+        inner_l = 8
+        segl = Segment(big, inner_l, 2, gen, a.mode)
+        kl = max(4, a.steps // 8)
+        msl, ll = time_device(big, segl, kl, 3, ctx)
         usl = msl * 1e3 / ll
-        ach = big.step_bytes * nl / (usl * 1e-6) / 1e9
+        spl = kl * inner_l // ll
+        ach = big.rollout_bytes(spl) * nl / (usl * 1e-6) / 1e9
         extra['roofline_hbm_resident_off'] = {
-            'envs': nl, 'state_bytes': int(big.state.numel() * 4), 'us_per_launch': usl, 'achieved': ach,
-            'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'env_steps_per_s': nl / (usl * 1e-6)}
+            'envs': nl, 'state_bytes': int(big.state.numel() * 4), 'env_steps_per_launch': spl * nl,
+            'us_per_launch': usl, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'env_steps_per_s': kl * inner_l * nl / (msl * 1e-3)}
         del big, segl
 
     stats = env.episode_stats().cpu().tolist()
@@ -399,6 +409,7 @@ def main():
     p.add_argument('--env-id', default=ENV_ID)
     p.add_argument('--num-envs', type=int, default=65536, help='environments per GPU')
     p.add_argument('--inner', type=int, default=64, help='env.steps per bench step (rollout segment)')
+    p.add_argument('--mode', default='fused', choices=['fused', 'per-step'])
     p.add_argument('--seed', type=int, default=0)
     p.add_argument('--cpu-seconds', type=float, default=10.0)
     p.add_argument('--no-cpu-baseline', action='store_true')
