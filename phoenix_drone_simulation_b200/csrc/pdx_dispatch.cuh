@@ -2,6 +2,7 @@
 // switch.  Included by one translation unit per arithmetic type / physics so that the
 // float64 parity kernels can be compiled with -fmad=false and the build parallelised.
 #pragma once
+#include <cstdlib>
 #include "pdx_kernels.cuh"
 
 namespace pdx {
@@ -60,6 +61,10 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
 template <class T>
 static int pick_block(int D, int NW, int C) {
   int block = 128;
+  if (const char* e = getenv("PDX_BLOCK")) {          // tuning hook: 32 / 64 / 128 / 256
+    const int b = atoi(e);
+    if (b == 32 || b == 64 || b == 128 || b == 256) block = b;
+  }
   while (block > 32 && rollout_smem_bytes<T>(block, D, NW, C) > (size_t)200 * 1024) block >>= 1;
   return block;
 }

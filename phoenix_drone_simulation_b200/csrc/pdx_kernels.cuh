@@ -338,22 +338,29 @@ __device__ __forceinline__ void fence_async_smem() {
 
 // Shared-memory plan of k_rollout (dynamic shared memory, in units of T):
 //   tile0, tile1 : [B][D]          observation rows of the block, layout == global slice
-//   slots        : [SW][kSlots]    reset hand-over, SW = NW + 2C words per slot (SoA over slots)
-//   park         : [NW][kSlots]    registers of the resetting lanes while they work for others
-// followed by   int  warp_cnt[kMaxBlock / 32];  double stats[8];
+//   hand_in      : [kIn][B]        what a reset needs from the finished env (indexed by thread)
+//   slots        : [SW][kSlots]    result of a reset, SW = NW + 2C words per slot (SoA over slots)
+//   park         : [NW][kSlots]    registers of the service lanes while they work for others
+// followed by   unsigned ballots[kMaxBlock / 32];  double acc[8][kSlots]  (episode statistics,
+// one accumulator column per service lane, reduced once at the end of the launch);
+// unsigned char owner[kMaxBlock]  (per warp: lanes that finished, in lane order).
+constexpr int kIn = 9;             // ep_return, ep_length, stale body rates 3, gyro bias 3, ref offset
+template <class T>
+__host__ __device__ inline size_t rollout_smem_words(int block, int D, int NW, int C) {
+  return (size_t)2 * block * D + (size_t)kIn * block + (size_t)(NW + 2 * C) * kSlots + (size_t)NW * kSlots;
+}
 template <class T>
 __host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int NW, int C) {
-  size_t words = (size_t)2 * block * D + (size_t)(NW + 2 * C) * kSlots + (size_t)NW * kSlots;
-  size_t bytes = words * sizeof(T);
+  size_t bytes = rollout_smem_words<T>(block, D, NW, C) * sizeof(T);
   bytes = (bytes + 15) & ~(size_t)15;
-  return bytes + sizeof(int) * (kMaxBlock / 32) + 8 + sizeof(double) * 8;
+  return bytes + sizeof(unsigned) * (kMaxBlock / 32) + sizeof(double) * 8 * kSlots + kMaxBlock;
 }
 
 // ---------------------------------------------------------------------------------------------
 //  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
-__global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
+__global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH, NW = Mo::NW;
@@ -370,12 +377,18 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile0 = reinterpret_cast<T*>(smem_raw);
   T* tile1 = tile0 + (size_t)B * D;
-  T* slots = tile1 + (size_t)B * D;
+  T* hand_in = tile1 + (size_t)B * D;
+  T* slots = hand_in + (size_t)kIn * B;
   T* park = slots + SW * kSlots;
-  size_t off = ((size_t)(park + NW * kSlots - tile0) * sizeof(T) + 15) & ~(size_t)15;
-  int* s_warp_cnt = reinterpret_cast<int*>(smem_raw + off);
-  double* s_stats = reinterpret_cast<double*>(smem_raw + off + sizeof(int) * (kMaxBlock / 32) + 8);
-  if (tid < 8) s_stats[tid] = (tid == 4 || tid == 6) ? 1e300 : (tid == 5 || tid == 7) ? -1e300 : 0.0;
+  const size_t off = (rollout_smem_words<T>(B, D, NW, C) * sizeof(T) + 15) & ~(size_t)15;
+  unsigned* s_ballot = reinterpret_cast<unsigned*>(smem_raw + off);
+  double* s_acc = reinterpret_cast<double*>(smem_raw + off + sizeof(unsigned) * (kMaxBlock / 32));
+  unsigned char* s_owner = reinterpret_cast<unsigned char*>(s_acc + 8 * kSlots);
+  if (tid < kSlots) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_acc[k * kSlots + tid] = (k == 4 || k == 6) ? 1e300 : (k == 5 || k == 7) ? -1e300 : 0.0;
+  }
+  const int n_warps = B >> 5;
 
   Mo m(c);
   T* state = reinterpret_cast<T*>(a.b.state);
@@ -397,6 +410,10 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
   bool block_any = false;
   const bool latency = Mo::BULLET && c.use_latency;
   T* w = m.w;
+  // the action of step t+1 is requested while step t computes (an L2/HBM miss otherwise sits at
+  // the head of every step's dependency chain)
+  float4 a_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) a_next = reinterpret_cast<const float4*>(a.actions)[i];
 
   for (int t = 0; t < a.n_steps; ++t) {
     T* tn = (t & 1) ? my_row1 : my_row0;             // this step's row, previous step's row
@@ -409,7 +426,8 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
     int n_ep = 0;
 
     if (valid) {
-      const float4 a4 = reinterpret_cast<const float4*>(a.actions)[tn_off + i];
+      const float4 a4 = a_next;
+      if (t + 1 < a.n_steps) a_next = reinterpret_cast<const float4*>(a.actions)[tn_off + n + i];
       const float act[4] = {a4.x, a4.y, a4.z, a4.w};
       const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter + (uint64_t)t, i,
                                                a.b.tape_step ? a.b.tape_step + (int64_t)t * c.slots_step * n : nullptr,
@@ -507,9 +525,32 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
       if (a.b.episode_length) a.b.episode_length[tn_off + i] = fin ? ep_len_out : 0;
     }
 
-    // ---- block vote.  This barrier also orders the row writes below after the bulk copy that
-    // last read this tile (thread 0 waited for it right after issuing the previous copy).
-    const int any_fin = __syncthreads_or(fin ? 1 : 0);
+    // ---- block vote: every warp publishes which lanes finished an episode; finished lanes leave
+    // what their reset needs.  This barrier also orders the row writes below after the bulk
+    // copy that last read this tile (thread 0 waited for it right after issuing the previous one).
+    const unsigned ballot = __ballot_sync(0xffffffffu, fin);
+    if (lane == 0) s_ballot[warp] = ballot;
+    if (fin) {
+      s_owner[warp * 32 + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)lane;
+      T stale[3];
+      m.body_rates(stale);
+      hand_in[0 * B + tid] = ep_ret_out;
+      hand_in[1 * B + tid] = (T)ep_len_out;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) hand_in[(2 + k) * B + tid] = stale[k];
+      if constexpr (NOISE) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) hand_in[(5 + k) * B + tid] = w[L.gyro_bias + k];
+      }
+      if constexpr (TASK == PDX_TASK_CIRCLE) hand_in[8 * B + tid] = w[L.ref_offset];
+    }
+    __syncthreads();
+    int total = 0, my_rank = __popc(ballot & ((1u << lane) - 1u));
+    for (int wv = 0; wv < n_warps; ++wv) {
+      const int cnt = __popc(s_ballot[wv]);
+      if (wv < warp) my_rank += cnt;
+      total += cnt;
+    }
 
     if (valid) {
       // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319)
@@ -528,106 +569,74 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
       for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
     }
 
-    // ---- auto-reset of finished episodes, compacted over the block
-    if (any_fin) {
+    // ---- auto-reset of finished episodes, compacted over the block: the lanes of one warp (a
+    // different one every step, so that the work spreads over the SM's four schedulers) each
+    // reset one finished environment; the others wait at the barrier.
+    if (total > 0) {
       block_any = true;
       const bool do_reset = fin && c.auto_reset;
-      const unsigned ballot = __ballot_sync(0xffffffffu, fin);
-      if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
-      __syncthreads();
-      int my_rank = __popc(ballot & ((1u << lane) - 1u)), total = 0;
-      for (int wv = 0; wv < (B >> 5); ++wv) {
-        const int cnt = s_warp_cnt[wv];
-        if (wv < warp) my_rank += cnt;
-        total += cnt;
-      }
+      const int service_warp = (int)((t + blockIdx.x) % n_warps);
       if (do_reset && a.b.final_obs) {                       // last observation of the episode
         T* fo = reinterpret_cast<T*>(a.b.final_obs) + (tn_off + i) * D;
         for (int k = 0; k < D; ++k) fo[k] = tn[k];
       }
       for (int chunk = 0; chunk < total; chunk += kSlots) {
-        const bool mine = fin && my_rank >= chunk && my_rank < chunk + kSlots;
-        const int sl = my_rank - chunk;
-        if (mine) {                                          // hand-over: what a reset needs
-          T stale[3];
-          m.body_rates(stale);
-          slots[0 * kSlots + sl] = (T)tid;
-          slots[1 * kSlots + sl] = ep_ret_out;
-          slots[2 * kSlots + sl] = (T)ep_len_out;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) slots[(3 + k) * kSlots + sl] = stale[k];
-          if constexpr (NOISE) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) slots[(6 + k) * kSlots + sl] = w[L.gyro_bias + k];
-          }
-          if constexpr (TASK == PDX_TASK_CIRCLE) slots[9 * kSlots + sl] = w[L.ref_offset];
-        }
-        __syncthreads();
         const int cnt = min(kSlots, total - chunk);
-        if (warp == 0) {
-          double s_cnt = 0.0, s_ret = 0.0, s_ret2 = 0.0, s_len = 0.0;
-          double mn = 1e300, mx = -1e300, ln = 1e300, lx = -1e300;
-          if (lane < cnt) {
-            const int owner = (int)slots[0 * kSlots + lane];
-            const double ret = (double)slots[1 * kSlots + lane], len = (double)slots[2 * kSlots + lane];
-            s_cnt = 1.0; s_ret = ret; s_ret2 = ret * ret; s_len = len;
-            mn = mx = ret; ln = lx = len;
-            if (c.auto_reset) {
-              // park my own environment, become a scratch environment for the owner's reset
-#pragma unroll
-              for (int k = 0; k < NW; ++k) park[k * kSlots + lane] = w[k];
-              T stale[3], o1[C], o2[C];
-#pragma unroll
-              for (int k = 0; k < NW; ++k) w[k] = T(0);
-#pragma unroll
-              for (int k = 0; k < 3; ++k) stale[k] = slots[(3 + k) * kSlots + lane];
-              if constexpr (NOISE) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) w[L.gyro_bias + k] = slots[(6 + k) * kSlots + lane];
-              }
-              if constexpr (TASK == PDX_TASK_CIRCLE) w[L.ref_offset] = slots[9 * kSlots + lane];
-              // nominal parameters are what a reset without domain randomisation leaves behind
-              w[L.dt] = c.time_step; w[L.mass] = c.mass; w[L.ftf1] = c.ftf1;
-#pragma unroll
-              for (int k = 0; k < 3; ++k) w[L.inertia + k] = c.inertia[k];
-              if constexpr (Mo::BULLET) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { w[L.motor_b + k] = T(1) * c.time_step / c.motor_tc; w[L.motor_k + k] = c.max_thrust; }
-              }
-              const int64_t io = block_base + owner;
-              const Rng<T, RNG> rr = make_rng<T, RNG>(a, a.counter + (uint64_t)t, io,
-                                                      a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
-                                                      a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
-              reset_env(m, rr, stale, o1, o2);
-#pragma unroll
-              for (int k = 0; k < NW; ++k) slots[k * kSlots + lane] = w[k];
-#pragma unroll
-              for (int k = 0; k < C; ++k) { slots[(NW + k) * kSlots + lane] = o1[k]; slots[(NW + C + k) * kSlots + lane] = o2[k]; }
-#pragma unroll
-              for (int k = 0; k < NW; ++k) w[k] = park[k * kSlots + lane];
-            }
+        if (warp == service_warp && lane < cnt) {
+          // owner of the (chunk + lane)-th finished environment of the block
+          int rank = chunk + lane, owner = 0;
+          for (int wv = 0; wv < n_warps; ++wv) {
+            const int pc = __popc(s_ballot[wv]);
+            if (rank >= 0 && rank < pc) owner = wv * 32 + (int)s_owner[wv * 32 + rank];
+            rank -= pc;
           }
+          const double ret = (double)hand_in[0 * B + owner], len = (double)hand_in[1 * B + owner];
           if (a.b.episode_stats) {
+            s_acc[0 * kSlots + lane] += 1.0; s_acc[1 * kSlots + lane] += ret;
+            s_acc[2 * kSlots + lane] += ret * ret; s_acc[3 * kSlots + lane] += len;
+            s_acc[4 * kSlots + lane] = fmin(s_acc[4 * kSlots + lane], ret);
+            s_acc[5 * kSlots + lane] = fmax(s_acc[5 * kSlots + lane], ret);
+            s_acc[6 * kSlots + lane] = fmin(s_acc[6 * kSlots + lane], len);
+            s_acc[7 * kSlots + lane] = fmax(s_acc[7 * kSlots + lane], len);
+          }
+          if (c.auto_reset) {
+            // park my own environment, become a scratch environment for the owner's reset
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s_cnt += __shfl_xor_sync(0xffffffffu, s_cnt, o);
-              s_ret += __shfl_xor_sync(0xffffffffu, s_ret, o);
-              s_ret2 += __shfl_xor_sync(0xffffffffu, s_ret2, o);
-              s_len += __shfl_xor_sync(0xffffffffu, s_len, o);
-              mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-              mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-              ln = fmin(ln, __shfl_xor_sync(0xffffffffu, ln, o));
-              lx = fmax(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+            for (int k = 0; k < NW; ++k) park[k * kSlots + lane] = w[k];
+            T stale[3], o1[C], o2[C];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = T(0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) stale[k] = hand_in[(2 + k) * B + owner];
+            if constexpr (NOISE) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) w[L.gyro_bias + k] = hand_in[(5 + k) * B + owner];
             }
-            if (lane == 0) {
-              s_stats[0] += s_cnt; s_stats[1] += s_ret; s_stats[2] += s_ret2; s_stats[3] += s_len;
-              s_stats[4] = fmin(s_stats[4], mn); s_stats[5] = fmax(s_stats[5], mx);
-              s_stats[6] = fmin(s_stats[6], ln); s_stats[7] = fmax(s_stats[7], lx);
+            if constexpr (TASK == PDX_TASK_CIRCLE) w[L.ref_offset] = hand_in[8 * B + owner];
+            // nominal parameters are what a reset without domain randomisation leaves behind
+            w[L.dt] = c.time_step; w[L.mass] = c.mass; w[L.ftf1] = c.ftf1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[L.inertia + k] = c.inertia[k];
+            if constexpr (Mo::BULLET) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { w[L.motor_b + k] = T(1) * c.time_step / c.motor_tc; w[L.motor_k + k] = c.max_thrust; }
             }
+            const int64_t io = block_base + owner;
+            const Rng<T, RNG> rr = make_rng<T, RNG>(a, a.counter + (uint64_t)t, io,
+                                                    a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
+                                                    a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
+            reset_env(m, rr, stale, o1, o2);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) slots[k * kSlots + lane] = w[k];
+#pragma unroll
+            for (int k = 0; k < C; ++k) { slots[(NW + k) * kSlots + lane] = o1[k]; slots[(NW + C + k) * kSlots + lane] = o2[k]; }
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = park[k * kSlots + lane];
           }
         }
         __syncthreads();
-        if (mine && do_reset) {                              // take the new episode back
+        if (do_reset && my_rank >= chunk && my_rank < chunk + kSlots) {      // take the new episode back
+          const int sl = my_rank - chunk;
 #pragma unroll
           for (int k = 0; k < NW; ++k) {
             if (!(k >= L.ou && k < L.ou + 4)) w[k] = slots[k * kSlots + sl];   // OU state survives
@@ -669,16 +678,28 @@ __global__ void __launch_bounds__(kMaxBlock) k_rollout(const KArgs<T> a) {
     const T* last = ((a.n_steps - 1) & 1) ? my_row1 : my_row0;
     store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) { return last[(s + 1) * E + idx]; });
   }
-  if (tid == 0) {
-    if (block_any && a.b.episode_stats) {
-      double* gs = a.b.episode_stats;
-      atomicAdd(&gs[0], s_stats[0]); atomicAdd(&gs[1], s_stats[1]); atomicAdd(&gs[2], s_stats[2]);
-      atomicAdd(&gs[3], s_stats[3]);
-      atomic_min_double(&gs[4], s_stats[4]); atomic_max_double(&gs[5], s_stats[5]);
-      atomic_min_double(&gs[6], s_stats[6]); atomic_max_double(&gs[7], s_stats[7]);
+  __syncthreads();
+  if (warp == 0 && block_any && a.b.episode_stats) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s_acc[k * kSlots + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[4] = fmin(v[4], __shfl_xor_sync(0xffffffffu, v[4], o));
+      v[5] = fmax(v[5], __shfl_xor_sync(0xffffffffu, v[5], o));
+      v[6] = fmin(v[6], __shfl_xor_sync(0xffffffffu, v[6], o));
+      v[7] = fmax(v[7], __shfl_xor_sync(0xffffffffu, v[7], o));
     }
-    bulk_wait_all();
+    if (lane == 0) {
+      double* gs = a.b.episode_stats;
+      atomicAdd(&gs[0], v[0]); atomicAdd(&gs[1], v[1]); atomicAdd(&gs[2], v[2]); atomicAdd(&gs[3], v[3]);
+      atomic_min_double(&gs[4], v[4]); atomic_max_double(&gs[5], v[5]);
+      atomic_min_double(&gs[6], v[6]); atomic_max_double(&gs[7], v[7]);
+    }
   }
+  if (tid == 0) bulk_wait_all();
 }
 
 }  // namespace pdx
