@@ -65,7 +65,7 @@ static int pick_block(int D, int NW, int C) {
     const int b = atoi(e);
     if (b == 32 || b == 64 || b == 128 || b == 256) block = b;
   }
-  while (block > 32 && rollout_smem_bytes<T>(block, D, NW, C) > (size_t)200 * 1024) block >>= 1;
+  while (block > 32 && rollout_smem_bytes<T>(block, D) > (size_t)200 * 1024) block >>= 1;
   return block;
 }
 
@@ -81,7 +81,7 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     return cudaGetLastError();
   }
   const int block = pick_block<T>(ka.c.obs_dim, Mo::NW, Mo::C);
-  const size_t smem = rollout_smem_bytes<T>(block, ka.c.obs_dim, Mo::NW, Mo::C);
+  const size_t smem = rollout_smem_bytes<T>(block, ka.c.obs_dim);
   if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
   static size_t smem_set[16] = {0};                 // per device: opt-in dynamic shared memory
   const int dev = ka.b.device & 15;

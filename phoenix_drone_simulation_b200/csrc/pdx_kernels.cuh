@@ -18,7 +18,6 @@
 namespace pdx {
 
 constexpr int kMaxBlock = 256;     // threads per block are chosen at run time (<= kMaxBlock)
-constexpr int kSlots = 32;         // reset slots per pass = lanes of warp 0
 
 template <class T>
 struct KArgs {
@@ -59,8 +58,8 @@ template <class T> __device__ __forceinline__ T unif(T lo, T hi, T u) { return l
 //  Outputs: m.w (complete new state, OU words untouched), o1 / o2 = the two observation calls
 //  (base.py:420,429); the history is H-1 copies of (o1, last_action) and one (o2, last_action).
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
-__device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, const Rng<T, RNG>& rng,
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, class RG>
+__device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, const RG& rng,
                                           const T stale[3], T* o1, T* o2) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
@@ -104,9 +103,9 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
       rpy[2] = unif(-(T(2) * pi), T(2) * pi, u[6]);
     } else {                                             // circle.py:213-256
       // np.random.randint(0, 300): the tape holds the integer itself; Philox: floor(300 u)
-      const bool from_tape = RNG == PDX_RNG_TAPE && !rng.dump;
+      const bool from_tape = RG::kTape && !rng.dumping();
       ref_off = from_tape ? (int)u[0] : min(299, (int)(u[0] * T(300)));
-      if (RNG == PDX_RNG_TAPE && rng.dump) rng.dump[0] = (double)ref_off;
+      rng.dump_value(0, (double)ref_off);
       T tp[3];
       m.ref_point(ref_off, tp);
       const T a0 = pi * T(20) / T(180), lim = pi * T(50) / T(180);
@@ -336,24 +335,18 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Shared-memory plan of k_rollout (dynamic shared memory, in units of T):
-//   tile0, tile1 : [B][D]          observation rows of the block, layout == global slice
-//   hand_in      : [kIn][B]        what a reset needs from the finished env (indexed by thread)
-//   slots        : [SW][kSlots]    result of a reset, SW = NW + 2C words per slot (SoA over slots)
-//   park         : [NW][kSlots]    registers of the service lanes while they work for others
-// followed by   unsigned ballots[kMaxBlock / 32];  double acc[8][kSlots]  (episode statistics,
-// one accumulator column per service lane, reduced once at the end of the launch);
-// unsigned char owner[kMaxBlock]  (per warp: lanes that finished, in lane order).
-constexpr int kIn = 9;             // ep_return, ep_length, stale body rates 3, gyro bias 3, ref offset
+// Shared-memory plan of k_rollout (dynamic shared memory):
+//   T tile0, tile1 [B][D]                     observation rows of the block, layout == global slice
+//   T rtab [B/32][kResetRows*4][kResetChunk]  per warp: reset draws of up to kResetChunk finished envs
+//   double acc_sum [4][B], T acc_ext [4][B]   per-thread episode statistics (n, sum ret, sum ret^2,
+//                                             sum len; min/max ret, min/max len), reduced once
+//   int tile_free                             last step whose bulk copy is known to have left its tile
+//   unsigned char fin_lane [B]                per warp: lanes that finished this step, in lane order
 template <class T>
-__host__ __device__ inline size_t rollout_smem_words(int block, int D, int NW, int C) {
-  return (size_t)2 * block * D + (size_t)kIn * block + (size_t)(NW + 2 * C) * kSlots + (size_t)NW * kSlots;
-}
-template <class T>
-__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int NW, int C) {
-  size_t bytes = rollout_smem_words<T>(block, D, NW, C) * sizeof(T);
+__host__ __device__ inline size_t rollout_smem_bytes(int block, int D) {
+  size_t bytes = ((size_t)2 * block * D + (size_t)(block / 32) * kResetRows * 4 * kResetChunk + (size_t)4 * block) * sizeof(T);
   bytes = (bytes + 15) & ~(size_t)15;
-  return bytes + sizeof(unsigned) * (kMaxBlock / 32) + sizeof(double) * 8 * kSlots + kMaxBlock;
+  return bytes + sizeof(double) * 4 * block + 16 + kMaxBlock;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -363,8 +356,7 @@ template <class T, int TASK, int PHYS, bool NOISE, int RNG>
 __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   constexpr Layout L = Mo::L;
-  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH, NW = Mo::NW;
-  constexpr int SW = NW + 2 * C;
+  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
   const DevCfg<T>& c = a.c;
   const int64_t n = a.b.n_envs;
   const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -377,18 +369,19 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile0 = reinterpret_cast<T*>(smem_raw);
   T* tile1 = tile0 + (size_t)B * D;
-  T* hand_in = tile1 + (size_t)B * D;
-  T* slots = hand_in + (size_t)kIn * B;
-  T* park = slots + SW * kSlots;
-  const size_t off = (rollout_smem_words<T>(B, D, NW, C) * sizeof(T) + 15) & ~(size_t)15;
-  unsigned* s_ballot = reinterpret_cast<unsigned*>(smem_raw + off);
-  double* s_acc = reinterpret_cast<double*>(smem_raw + off + sizeof(unsigned) * (kMaxBlock / 32));
-  unsigned char* s_owner = reinterpret_cast<unsigned char*>(s_acc + 8 * kSlots);
-  if (tid < kSlots) {
+  T* rtab = tile1 + (size_t)B * D + (size_t)warp * (kResetRows * 4 * kResetChunk);
+  T* acc_ext = tile1 + (size_t)B * D + (size_t)(B >> 5) * (kResetRows * 4 * kResetChunk);
+  const size_t off = (((size_t)2 * B * D + (size_t)(B >> 5) * kResetRows * 4 * kResetChunk + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
+  double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
+  volatile int* s_tile_free = reinterpret_cast<volatile int*>(smem_raw + off + sizeof(double) * 4 * B);
+  unsigned char* s_fin_lane = smem_raw + off + sizeof(double) * 4 * B + 16 + (warp << 5);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s_acc[k * kSlots + tid] = (k == 4 || k == 6) ? 1e300 : (k == 5 || k == 7) ? -1e300 : 0.0;
+  for (int k = 0; k < 4; ++k) {
+    acc_sum[k * B + tid] = 0.0;
+    acc_ext[k * B + tid] = (k & 1) ? T(-1e30) : T(1e30);
   }
-  const int n_warps = B >> 5;
+  if (tid == 0) *s_tile_free = -1;
+  __syncthreads();
 
   Mo m(c);
   T* state = reinterpret_cast<T*>(a.b.state);
@@ -407,7 +400,7 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       }
     }
   }
-  bool block_any = false;
+  bool any_fin = false;
   const bool latency = Mo::BULLET && c.use_latency;
   T* w = m.w;
   // the action of step t+1 is requested while step t computes (an L2/HBM miss otherwise sits at
@@ -525,32 +518,9 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       if (a.b.episode_length) a.b.episode_length[tn_off + i] = fin ? ep_len_out : 0;
     }
 
-    // ---- block vote: every warp publishes which lanes finished an episode; finished lanes leave
-    // what their reset needs.  This barrier also orders the row writes below after the bulk
-    // copy that last read this tile (thread 0 waited for it right after issuing the previous one).
-    const unsigned ballot = __ballot_sync(0xffffffffu, fin);
-    if (lane == 0) s_ballot[warp] = ballot;
-    if (fin) {
-      s_owner[warp * 32 + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)lane;
-      T stale[3];
-      m.body_rates(stale);
-      hand_in[0 * B + tid] = ep_ret_out;
-      hand_in[1 * B + tid] = (T)ep_len_out;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) hand_in[(2 + k) * B + tid] = stale[k];
-      if constexpr (NOISE) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) hand_in[(5 + k) * B + tid] = w[L.gyro_bias + k];
-      }
-      if constexpr (TASK == PDX_TASK_CIRCLE) hand_in[8 * B + tid] = w[L.ref_offset];
-    }
-    __syncthreads();
-    int total = 0, my_rank = __popc(ballot & ((1u << lane) - 1u));
-    for (int wv = 0; wv < n_warps; ++wv) {
-      const int cnt = __popc(s_ballot[wv]);
-      if (wv < warp) my_rank += cnt;
-      total += cnt;
-    }
+    // ---- the tile of this step was last read by the bulk copy of step t-2: thread 0 publishes
+    // the newest step whose copy has drained (it waits right after issuing each copy)
+    if (t >= 2) { while (*s_tile_free < t - 2) {} }
 
     if (valid) {
       // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319)
@@ -569,87 +539,79 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
     }
 
-    // ---- auto-reset of finished episodes, compacted over the block: the lanes of one warp (a
-    // different one every step, so that the work spreads over the SM's four schedulers) each
-    // reset one finished environment; the others wait at the barrier.
-    if (total > 0) {
-      block_any = true;
-      const bool do_reset = fin && c.auto_reset;
-      const int service_warp = (int)((t + blockIdx.x) % n_warps);
-      if (do_reset && a.b.final_obs) {                       // last observation of the episode
+    // ---- auto-reset of finished episodes.  The reset path is as long as a step, mostly random
+    // number generation, and only a few lanes of a warp need it: the warp generates the draws of
+    // its finished environments TOGETHER (one Philox call per lane and pass, into a shared table)
+    // and only the remaining arithmetic runs divergent on the owner lanes.  No block barrier.
+    if (fin) {
+      any_fin = true;
+      acc_sum[0 * B + tid] += 1.0;
+      acc_sum[1 * B + tid] += (double)ep_ret_out;
+      acc_sum[2 * B + tid] += (double)ep_ret_out * (double)ep_ret_out;
+      acc_sum[3 * B + tid] += (double)ep_len_out;
+      acc_ext[0 * B + tid] = M<T>::fmin(acc_ext[0 * B + tid], ep_ret_out);
+      acc_ext[1 * B + tid] = M<T>::fmax(acc_ext[1 * B + tid], ep_ret_out);
+      acc_ext[2 * B + tid] = M<T>::fmin(acc_ext[2 * B + tid], (T)ep_len_out);
+      acc_ext[3 * B + tid] = M<T>::fmax(acc_ext[3 * B + tid], (T)ep_len_out);
+    }
+    const bool do_reset = fin && c.auto_reset;
+    const unsigned ballot = __ballot_sync(0xffffffffu, do_reset);
+    if (ballot) {
+      if (do_reset && a.b.final_obs) {                     // last observation of the episode
         T* fo = reinterpret_cast<T*>(a.b.final_obs) + (tn_off + i) * D;
         for (int k = 0; k < D; ++k) fo[k] = tn[k];
       }
-      for (int chunk = 0; chunk < total; chunk += kSlots) {
-        const int cnt = min(kSlots, total - chunk);
-        if (warp == service_warp && lane < cnt) {
-          // owner of the (chunk + lane)-th finished environment of the block
-          int rank = chunk + lane, owner = 0;
-          for (int wv = 0; wv < n_warps; ++wv) {
-            const int pc = __popc(s_ballot[wv]);
-            if (rank >= 0 && rank < pc) owner = wv * 32 + (int)s_owner[wv * 32 + rank];
-            rank -= pc;
-          }
-          const double ret = (double)hand_in[0 * B + owner], len = (double)hand_in[1 * B + owner];
-          if (a.b.episode_stats) {
-            s_acc[0 * kSlots + lane] += 1.0; s_acc[1 * kSlots + lane] += ret;
-            s_acc[2 * kSlots + lane] += ret * ret; s_acc[3 * kSlots + lane] += len;
-            s_acc[4 * kSlots + lane] = fmin(s_acc[4 * kSlots + lane], ret);
-            s_acc[5 * kSlots + lane] = fmax(s_acc[5 * kSlots + lane], ret);
-            s_acc[6 * kSlots + lane] = fmin(s_acc[6 * kSlots + lane], len);
-            s_acc[7 * kSlots + lane] = fmax(s_acc[7 * kSlots + lane], len);
-          }
-          if (c.auto_reset) {
-            // park my own environment, become a scratch environment for the owner's reset
-#pragma unroll
-            for (int k = 0; k < NW; ++k) park[k * kSlots + lane] = w[k];
-            T stale[3], o1[C], o2[C];
-#pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = T(0);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) stale[k] = hand_in[(2 + k) * B + owner];
-            if constexpr (NOISE) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) w[L.gyro_bias + k] = hand_in[(5 + k) * B + owner];
+      const uint64_t ctr = a.counter + (uint64_t)t;
+      T o1[C], o2[C], stale[3];
+      if (do_reset) m.body_rates(stale);
+      if constexpr (RNG == PDX_RNG_PHILOX) {
+        const int my_rank = __popc(ballot & ((1u << lane) - 1u));
+        const int total = __popc(ballot);
+        if (do_reset) s_fin_lane[my_rank] = (unsigned char)lane;
+        __syncwarp();
+        for (int chunk = 0; chunk < total; chunk += kResetChunk) {
+          const int cnt = min(kResetChunk, total - chunk);
+          // work item = (site row, finished env): consecutive lanes take consecutive envs
+          for (int item = lane; item < cnt * kResetRows; item += 32) {
+            const int row = item / cnt, slot = item - row * cnt;
+            const uint32_t site = SITE_RESET + (uint32_t)row;
+            if (!reset_site_used(site, TASK, Mo::BULLET, NOISE)) continue;
+            const int owner = (int)s_fin_lane[chunk + slot];
+            Rng<T, RNG> rr = make_rng<T, RNG>(a, ctr, block_base + (warp << 5) + owner, nullptr, nullptr);
+            const uint4 r4 = rr.raw(site);
+            T v[4];
+            if (reset_site_is_normal(site)) {
+              M<T>::box_muller(r4.x, r4.y, &v[0], &v[1]);
+              M<T>::box_muller(r4.z, r4.w, &v[2], &v[3]);
+            } else {
+              v[0] = M<T>::unit(r4.x); v[1] = M<T>::unit(r4.y); v[2] = M<T>::unit(r4.z); v[3] = M<T>::unit(r4.w);
             }
-            if constexpr (TASK == PDX_TASK_CIRCLE) w[L.ref_offset] = hand_in[8 * B + owner];
-            // nominal parameters are what a reset without domain randomisation leaves behind
-            w[L.dt] = c.time_step; w[L.mass] = c.mass; w[L.ftf1] = c.ftf1;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) w[L.inertia + k] = c.inertia[k];
-            if constexpr (Mo::BULLET) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { w[L.motor_b + k] = T(1) * c.time_step / c.motor_tc; w[L.motor_k + k] = c.max_thrust; }
-            }
-            const int64_t io = block_base + owner;
-            const Rng<T, RNG> rr = make_rng<T, RNG>(a, a.counter + (uint64_t)t, io,
-                                                    a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
-                                                    a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
-            reset_env(m, rr, stale, o1, o2);
-#pragma unroll
-            for (int k = 0; k < NW; ++k) slots[k * kSlots + lane] = w[k];
-#pragma unroll
-            for (int k = 0; k < C; ++k) { slots[(NW + k) * kSlots + lane] = o1[k]; slots[(NW + C + k) * kSlots + lane] = o2[k]; }
-#pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = park[k * kSlots + lane];
+            for (int k = 0; k < 4; ++k) rtab[(row * 4 + k) * kResetChunk + slot] = v[k];
           }
+          __syncwarp();
+          if (do_reset && my_rank >= chunk && my_rank < chunk + kResetChunk) {
+            TableRng<T> tr;
+            tr.tab = rtab + (my_rank - chunk);
+            reset_env(m, tr, stale, o1, o2);
+          }
+          __syncwarp();
         }
-        __syncthreads();
-        if (do_reset && my_rank >= chunk && my_rank < chunk + kSlots) {      // take the new episode back
-          const int sl = my_rank - chunk;
-#pragma unroll
-          for (int k = 0; k < NW; ++k) {
-            if (!(k >= L.ou && k < L.ou + 4)) w[k] = slots[k * kSlots + sl];   // OU state survives
-          }
-          for (int j = 0; j < H; ++j) {
-            const int src = NW + (j == H - 1 ? C : 0);
-#pragma unroll
-            for (int k = 0; k < C; ++k) tn[j * E + k] = slots[(src + k) * kSlots + sl];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
-          }
+      } else {
+        if (do_reset) {
+          const Rng<T, RNG> rr = make_rng<T, RNG>(a, ctr, i,
+                                                  a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
+                                                  a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
+          reset_env(m, rr, stale, o1, o2);
         }
-        if (chunk + kSlots < total) __syncthreads();         // slots are reused by the next pass
+      }
+      if (do_reset) {                                      // first observation of the new episode
+        for (int j = 0; j < H; ++j) {
+#pragma unroll
+          for (int k = 0; k < C; ++k) tn[j * E + k] = (j == H - 1) ? o2[k] : o1[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
+        }
       }
     }
 
@@ -665,10 +627,12 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       if (tid == 0) {
         bulk_store(gdst, tile, bytes);
         bulk_wait_read<1>();          // the copy issued one step ago has finished reading its tile
+        *s_tile_free = t - 1;
       }
     } else {
       __syncthreads();
       for (int e = tid; e < rows * D; e += B) gdst[e] = tile[e];
+      if (tid == 0) *s_tile_free = t - 1;
     }
   }
 
@@ -678,25 +642,34 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
     const T* last = ((a.n_steps - 1) & 1) ? my_row1 : my_row0;
     store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) { return last[(s + 1) * E + idx]; });
   }
-  __syncthreads();
-  if (warp == 0 && block_any && a.b.episode_stats) {
-    double v[8];
+  if (a.b.episode_stats && __syncthreads_or(any_fin ? 1 : 0)) {
+    if (warp == 0) {
+      double v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = s_acc[k * kSlots + lane];
+      for (int k = 0; k < 8; ++k) v[k] = (k == 4 || k == 6) ? 1e300 : (k == 5 || k == 7) ? -1e300 : 0.0;
+      for (int col = lane; col < B; col += 32) {
+        if (acc_sum[col] > 0.0) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+          for (int k = 0; k < 4; ++k) v[k] += acc_sum[k * B + col];
+          v[4] = fmin(v[4], (double)acc_ext[0 * B + col]); v[5] = fmax(v[5], (double)acc_ext[1 * B + col]);
+          v[6] = fmin(v[6], (double)acc_ext[2 * B + col]); v[7] = fmax(v[7], (double)acc_ext[3 * B + col]);
+        }
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-      v[4] = fmin(v[4], __shfl_xor_sync(0xffffffffu, v[4], o));
-      v[5] = fmax(v[5], __shfl_xor_sync(0xffffffffu, v[5], o));
-      v[6] = fmin(v[6], __shfl_xor_sync(0xffffffffu, v[6], o));
-      v[7] = fmax(v[7], __shfl_xor_sync(0xffffffffu, v[7], o));
-    }
-    if (lane == 0) {
-      double* gs = a.b.episode_stats;
-      atomicAdd(&gs[0], v[0]); atomicAdd(&gs[1], v[1]); atomicAdd(&gs[2], v[2]); atomicAdd(&gs[3], v[3]);
-      atomic_min_double(&gs[4], v[4]); atomic_max_double(&gs[5], v[5]);
-      atomic_min_double(&gs[6], v[6]); atomic_max_double(&gs[7], v[7]);
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        v[4] = fmin(v[4], __shfl_xor_sync(0xffffffffu, v[4], o));
+        v[5] = fmax(v[5], __shfl_xor_sync(0xffffffffu, v[5], o));
+        v[6] = fmin(v[6], __shfl_xor_sync(0xffffffffu, v[6], o));
+        v[7] = fmax(v[7], __shfl_xor_sync(0xffffffffu, v[7], o));
+      }
+      if (lane == 0) {
+        double* gs = a.b.episode_stats;
+        atomicAdd(&gs[0], v[0]); atomicAdd(&gs[1], v[1]); atomicAdd(&gs[2], v[2]); atomicAdd(&gs[3], v[3]);
+        atomic_min_double(&gs[4], v[4]); atomic_max_double(&gs[5], v[5]);
+        atomic_min_double(&gs[6], v[6]); atomic_max_double(&gs[7], v[7]);
+      }
     }
   }
   if (tid == 0) bulk_wait_all();

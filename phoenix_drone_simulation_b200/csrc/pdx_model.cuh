@@ -335,7 +335,8 @@ struct Model {
 
   // One full compute_observation() -> core[C].  `site0`/`slot`: first draw site / tape slot.
   // `q_true`: quaternion to report when noise is off (drone.quaternion).
-  __device__ __forceinline__ void observe(const Rng<T, RNG>& rng, uint32_t site0, int slot,
+  template <class R>
+  __device__ __forceinline__ void observe(const R& rng, uint32_t site0, int slot,
                                           const T target[3], const T act[4], const T q_true[4],
                                           T core[C]) {
     const T* p = &w[L.xyz];
