@@ -227,45 +227,29 @@ def time_device(env, seg, K, W, dist_ctx):
 
 
 def time_e2e(env, inner, K, W, dist_ctx, gen_seed):
-    """Same metric through the public VecEnv API with HOST buffers: every env.step copies its
-    actions from pinned host memory, launches, and copies obs/reward/flags back to pinned host
-    memory; all of it inside the timed region."""
+    """Same metric through the public VecEnv API with HOST buffers (VecEnv.step_many_host): every
+    segment copies its actions from pinned host memory, runs, and copies obs / reward / cost /
+    flags back to pinned host memory, chunk-pipelined over three streams; all inside the timed
+    region."""
     import torch
-    n, d = env.num_envs, env.obs_dim
+    chunk = 8 if inner % 8 == 0 else 1
+    pipe = env.make_host_pipeline(inner, chunk)
     g = torch.Generator().manual_seed(gen_seed)
-    h_act = (torch.rand((inner, n, 4), generator=g) * 2 - 1).pin_memory()
-    h_obs = torch.empty((n, d), dtype=env.dtype).pin_memory()
-    h_rew = torch.empty((n,), dtype=env.dtype).pin_memory()
-    h_flags = torch.empty((2, n), dtype=torch.uint8).pin_memory()
-    d_act = torch.empty((n, 4), dtype=torch.float32, device=env.device)
-    d_flags = torch.empty((2, n), dtype=torch.uint8, device=env.device)
-    out = {'terminated': d_flags[0], 'truncated': d_flags[1]}
-    h2d = h_act[0].numel() * 4
-    d2h = h_obs.numel() * h_obs.element_size() + h_rew.numel() * h_rew.element_size() + h_flags.numel()
-
-    def one(t):
-        d_act.copy_(h_act[t], non_blocking=True)
-        obs, rew, _, _, _ = env.step(d_act, out=out)
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_flags.copy_(d_flags, non_blocking=True)
-
+    pipe['host']['actions'].copy_(torch.rand(pipe['host']['actions'].shape, generator=g) * 2 - 1)
     for _ in range(W):
-        for t in range(inner):
-            one(t)
+        env.step_many_host(pipe)
     dist_ctx.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        for t in range(inner):
-            one(t)
+        env.step_many_host(pipe)
     e1.record()
     torch.cuda.synchronize()
     ms = dist_ctx.max_over_ranks(e0.elapsed_time(e1))
     dist_ctx.barrier()
-    assert torch.isfinite(h_obs).all()
-    return ms, h2d * inner, d2h * inner
+    assert torch.isfinite(pipe['host']['obs']).all()
+    return ms, pipe['h2d_bytes'], pipe['d2h_bytes']
 
 
 class DistCtx:
@@ -362,7 +346,7 @@ def run_gpu_arm(a):
     e2e_ms, h2d, d2h = time_e2e(env, a.inner, max(1, a.steps // a.e2e_div), a.warmup, ctx, 99 + ctx.rank)
     e2e_steps = max(1, a.steps // a.e2e_div) * a.inner * n * ctx.world
     e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'api': 'VecEnv.step with pinned host action/obs/reward/flag buffers, copies inside the timed region'}
+           'api': 'VecEnv.step_many_host: pinned host action/obs/reward/cost/flag buffers, H2D + launch + D2H per 8-step chunk on three streams, all inside the timed region'}
 
     extra = {}
     if a.large_envs and ctx.world == 1:

@@ -201,6 +201,11 @@ int pdx_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint
 int pdx_moments(int64_t rows, int32_t dim, const float* x, const double* shift,
                 double* out, void* stream);
 
+/* Cross-rank combination of the 8-word episode statistics (utils/mpi_tools.py:217-240 does four
+ * MPI all-reduces per key): the caller all-gathers the per-rank vectors into gathered[world][8]
+ * (one NCCL call) and this writes out[0..4) = sums, out[4], out[6] = minima, out[5], out[7] = maxima. */
+int pdx_stats_combine(int32_t world, const double* gathered, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

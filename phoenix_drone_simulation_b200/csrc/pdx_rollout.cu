@@ -68,6 +68,19 @@ __global__ void k_moments(int64_t rows, int dim, const float* __restrict__ x,
   }
 }
 
+// Combines the episode-statistics vectors of all ranks after one all-gather:
+// out[0..4) = column sums, out[4], out[6] = column minima, out[5], out[7] = column maxima.
+__global__ void k_stats_combine(int world, const double* __restrict__ gathered, double* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= 8) return;
+  double v = gathered[k];
+  for (int r = 1; r < world; ++r) {
+    const double x = gathered[r * 8 + k];
+    v = k < 4 ? v + x : ((k & 1) ? fmax(v, x) : fmin(v, x));
+  }
+  out[k] = v;
+}
+
 // The library carries its own static CUDA runtime: select the device the data lives on.
 int select_device_of(const void* ptr) {
   int ndev = 0;
@@ -108,5 +121,13 @@ extern "C" int pdx_moments(int64_t rows, int32_t dim, const float* x, const doub
   const unsigned grid = (unsigned)(tiles < 1184 ? tiles : 1184);      // 8 x 148 SMs
   const size_t smem = 2ull * bx * by * sizeof(double);
   k_moments<<<grid, block, smem, (cudaStream_t)stream>>>(rows, dim, x, shift, out);
+  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+}
+
+extern "C" int pdx_stats_combine(int32_t world, const double* gathered, double* out, void* stream) {
+  if (world <= 0 || !gathered || !out) return PDX_ERR_INVALID;
+  const int rc = select_device_of(gathered);
+  if (rc) return rc;
+  k_stats_combine<<<1, 32, 0, (cudaStream_t)stream>>>(world, gathered, out);
   return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
 }

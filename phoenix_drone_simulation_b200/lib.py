@@ -97,6 +97,7 @@ def load():
                             C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_moments.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pdx_stats_combine.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.pdx_abi_version() != ABI_VERSION:
         raise PhoenixB200Error(f'ABI mismatch: library {lib.pdx_abi_version()} != binding {ABI_VERSION}')
     if lib.pdx_config_size() != C.sizeof(PdxConfig) or lib.pdx_buffers_size() != C.sizeof(PdxBuffers):
@@ -115,5 +116,5 @@ EXPORTED_SYMBOLS = [
     'pdx_config_finalize', 'pdx_state_quads', 'pdx_state_field', 'pdx_tape_slots',
     'pdx_step_bytes', 'pdx_rollout_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step',
     'pdx_step_many', 'pdx_dump_draws',
-    'pdx_gae', 'pdx_moments',
+    'pdx_gae', 'pdx_moments', 'pdx_stats_combine',
 ]

@@ -185,6 +185,60 @@ class VecEnv:
         self._counter += T
         return out
 
+    def make_host_pipeline(self, n_steps, chunk_steps=8):
+        """Pinned host buffers + double-buffered device staging for `step_many_host`."""
+        T, c, n, d = int(n_steps), int(chunk_steps), self.num_envs, self.obs_dim
+        assert T % c == 0
+        dev, dt = self.device, self.dtype
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+        host = {'actions': pin(T, n, 4, dtype=torch.float32), 'obs': pin(T, n, d, dtype=dt),
+                'reward': pin(T, n, dtype=dt), 'cost': pin(T, n, dtype=dt),
+                'terminated': pin(T, n, dtype=torch.uint8), 'truncated': pin(T, n, dtype=torch.uint8)}
+        stage = [{'actions': torch.empty((c, n, 4), dtype=torch.float32, device=dev),
+                  'obs': torch.empty((c, n, d), dtype=dt, device=dev),
+                  'reward': torch.empty((c, n), dtype=dt, device=dev), 'cost': torch.empty((c, n), dtype=dt, device=dev),
+                  'terminated': torch.empty((c, n), dtype=torch.uint8, device=dev),
+                  'truncated': torch.empty((c, n), dtype=torch.uint8, device=dev)} for _ in range(2)]
+        streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        h2d_bytes = host['actions'].numel() * 4
+        d2h_bytes = sum(host[k].numel() * host[k].element_size() for k in host if k != 'actions')
+        return {'host': host, 'stage': stage, 'streams': streams, 'T': T, 'chunk': c,
+                'h2d_bytes': h2d_bytes, 'd2h_bytes': d2h_bytes}
+
+    def step_many_host(self, pipe):
+        """T env.steps with HOST action / result buffers (pipe['host'], pinned): the actions of
+        chunk k+1 travel host->device and the results of chunk k-1 device->host while chunk k
+        computes (three streams, two staging sets).  Returns after the copies are enqueued; the
+        caller synchronises (or records an event on the current stream, which waits for them)."""
+        host, stage, (s_in, s_run, s_out) = pipe['host'], pipe['stage'], pipe['streams']
+        T, c = pipe['T'], pipe['chunk']
+        cur = torch.cuda.current_stream(self.device)
+        for s in (s_in, s_run, s_out):
+            s.wait_stream(cur)
+        ev_in, ev_run, ev_out = {}, {}, {}
+        outs = ('obs', 'reward', 'cost', 'terminated', 'truncated')
+        for k in range(T // c):
+            st = stage[k & 1]
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_run[k - 2])          # staging actions consumed
+                st['actions'].copy_(host['actions'][k * c:(k + 1) * c], non_blocking=True)
+                ev_in[k] = s_in.record_event()
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in[k])
+                if k >= 2:
+                    s_run.wait_event(ev_out[k - 2])         # staging results drained
+                self.step_many(st['actions'], {o: st[o] for o in outs})
+                ev_run[k] = s_run.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[k])
+                for o in outs:
+                    host[o][k * c:(k + 1) * c].copy_(st[o], non_blocking=True)
+                ev_out[k] = s_out.record_event()
+        for s in (s_in, s_run, s_out):
+            cur.wait_stream(s)
+        return host
+
     def rollout_bytes(self, n_steps):
         """Algorithmic HBM bytes per environment of one n_steps launch (pdx_rollout_bytes)."""
         return int(self.lib.pdx_rollout_bytes(C.byref(self.pdx), int(n_steps)))
