@@ -263,6 +263,7 @@ class DistCtx:
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            os.environ['NCCL_DEBUG'] = os.environ.get('PDX_NCCL_DEBUG', 'WARN')   # keep stdout to ONE JSON line
             dist.init_process_group('nccl', device_id=self.device)
             self.dist = dist
         else:
