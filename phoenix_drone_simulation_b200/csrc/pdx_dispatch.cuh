@@ -2,6 +2,7 @@
 // switch.  Included by one translation unit per arithmetic type / physics so that the
 // float64 parity kernels can be compiled with -fmad=false and the build parallelised.
 #pragma once
+#include <cmath>
 #include <cstdlib>
 #include "pdx_kernels.cuh"
 
@@ -47,6 +48,7 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
   d.quat_std = (T)p.quat_norm_std; d.quat_unif = (T)p.quat_unif_range;
   d.gyro_pi = (T)p.gyro_pi; d.gyro_sigma_b = (T)p.gyro_sigma_b; d.gyro_rw = (T)p.gyro_random_walk;
   d.gyro_to = (T)p.gyro_turn_on;
+  d.gyro_white = (T)std::sqrt(p.gyro_random_walk * p.gyro_random_walk + p.gyro_turn_on * p.gyro_turn_on);
   d.pen_action = (T)p.penalty_action; d.pen_angle = (T)p.penalty_angle; d.pen_spin = (T)p.penalty_spin;
   d.pen_terminal = (T)p.penalty_terminal; d.pen_velocity = (T)p.penalty_velocity;
   d.arp = (T)p.action_rate_penalty;

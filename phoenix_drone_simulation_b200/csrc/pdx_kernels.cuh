@@ -74,6 +74,7 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
   T q[4] = {T(0), T(0), T(0), T(1)};
   T vel[3] = {T(0), T(0), T(0)};
   T oms[3] = {T(0), T(0), T(0)};
+  T rpy0[3] = {T(0), T(0), T(0)};                        // Euler angles the pose is built from
   int ref_off = 0;
   if constexpr (TASK == PDX_TASK_CIRCLE) ref_off = (int)w[L.ref_offset];
 
@@ -83,7 +84,8 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
       rng.template uniforms<3>(SITE_RESET, 0, u);
       pos[0] = f32q(pos[0] + unif(T(-0.25), T(0.25), u[0]));
       pos[1] = f32q(pos[1] + unif(T(-0.25), T(0.25), u[1]));
-      quat_from_euler(T(0), T(0), unif(-pi, pi, u[2]), q);
+      rpy0[2] = unif(-pi, pi, u[2]);
+      quat_from_euler(T(0), T(0), rpy0[2], q);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { la[k] = T(-1); ring[k] = T(-1); ring[4 + k] = T(-1); }
@@ -122,6 +124,8 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
     const T yl = pi * T(20) / T(180);
     oms[2] = unif(-yl, yl, u[13]);
     quat_from_euler(rpy[0], rpy[1], rpy[2], q);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rpy0[k] = rpy[k];
     T z[8];
     rng.template normals<8>(SITE_RESET + 4, 14, z);
 #pragma unroll
@@ -183,8 +187,16 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
     for (int k = 0; k < 3; ++k) w[L.omega_world + k] = ww[k];
     w[L.ring_idx] = T(0);
   } else {
+    // agents.py:446: rpy = getEulerFromQuaternion(q).  With |roll|, |pitch| < pi/2 (all reset
+    // distributions) that round trip is the identity up to wrapping yaw into (-pi, pi]; the
+    // float32 kernels use that, the float64 kernels do the reference's round trip.
     T e[3];
-    euler_from_quat(q, e);
+    if constexpr (sizeof(T) == 4) {
+      e[0] = rpy0[0]; e[1] = rpy0[1];
+      e[2] = rpy0[2] - T(6.283185307179586) * rintf(rpy0[2] * T(0.15915494309189535));
+    } else {
+      euler_from_quat(q, e);
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { w[L.rpy + k] = e[k]; w[L.omega + k] = ob[k]; }
   }
@@ -571,11 +583,19 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
         __syncwarp();
         for (int chunk = 0; chunk < total; chunk += kResetChunk) {
           const int cnt = min(kResetChunk, total - chunk);
-          // work item = (site row, finished env): consecutive lanes take consecutive envs
-          for (int item = lane; item < cnt * kResetRows; item += 32) {
-            const int row = item / cnt, slot = item - row * cnt;
+          // work item = (site row, finished env): consecutive lanes take consecutive envs.
+          // The rows a reset draws form four runs (task, DR, first and second observation call).
+          constexpr int n_task = TASK == PDX_TASK_TAKEOFF ? 1 : (Mo::BULLET ? 7 : 6);
+          constexpr int n_dr = Mo::BULLET ? 4 : 2, n_obs = NOISE ? 6 : 0;
+          constexpr int n_rows = n_task + n_dr + 2 * n_obs;
+          const unsigned rcp = (65536u + (unsigned)cnt - 1u) / (unsigned)cnt;
+          for (int item = lane; item < cnt * n_rows; item += 32) {
+            const int ri = (int)(((unsigned)item * rcp) >> 16), slot = item - ri * cnt;
+            const int row = ri < n_task ? ri
+                          : ri < n_task + n_dr ? (int)(SITE_DR - SITE_RESET) + ri - n_task
+                          : ri < n_task + n_dr + n_obs ? (int)(SITE_RESET_OBS1 - SITE_RESET) + ri - n_task - n_dr
+                          : (int)(SITE_RESET_OBS2 - SITE_RESET) + ri - n_task - n_dr - n_obs;
             const uint32_t site = SITE_RESET + (uint32_t)row;
-            if (!reset_site_used(site, TASK, Mo::BULLET, NOISE)) continue;
             const int owner = (int)s_fin_lane[chunk + slot];
             Rng<T, RNG> rr = make_rng<T, RNG>(a, ctr, block_base + (warp << 5) + owner, nullptr, nullptr);
             const uint4 r4 = rr.raw(site);

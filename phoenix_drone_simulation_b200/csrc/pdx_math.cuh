@@ -129,8 +129,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // Draw-site ids (4th counter word).  One Philox call per site id yields 4 words; a draw block
 // of K variates occupies ceil(K/4) consecutive ids.
 enum DrawSite : uint32_t {
-  SITE_SUBSTEP = 0,      // + 8*substep : +0..3  OU(4n) + gyro bias / random walk / turn-on (9n)
-  SITE_FINAL_OBS = 64,   // +0..4 normals: pos(3) vel(3) gyro(9) theta(3); +5,+6 uniforms: pos(3) theta(3)
+  SITE_SUBSTEP = 0,      // + 8*substep : +0..2  OU(4n) + gyro bias (3n) + gyro white noise (3n)
+  SITE_FINAL_OBS = 64,   // +0..3 normals: pos(3) vel(3) gyro bias(3) gyro white(3) theta(3); +4,+5 uniforms: pos(3) theta(3)
   SITE_RESET = 80,       // +0..3 task uniforms (<=14), +4..6 motor x / ring rows normals (4+8)
   SITE_DR = 88,          // +0..3 dt,m,Jx,Jy,Jz,ftf0,ftf1, motor T(4), T2W(4) uniforms
   SITE_RESET_OBS1 = 96,  // like SITE_FINAL_OBS
@@ -183,6 +183,11 @@ struct Rng {
       for (int k = 0; k < 4; ++k) if (4 * c + k < K) out[4 * c + k] = M<T>::unit(v[k]);
     }
   }
+  // Raw generation (no tape, no dump): what the production path consumes.
+  template <int K> __device__ __forceinline__ void gen_normals(uint32_t site0, T* out) const { philox_normals<K>(site0, out); }
+  template <int K> __device__ __forceinline__ void gen_uniforms(uint32_t site0, T* out) const { philox_uniforms<K>(site0, out); }
+  // true when the draws must be the reference's own (recorded) ones, one per reference draw
+  __device__ __forceinline__ bool exact_draws() const { return MODE == PDX_RNG_TAPE && dump == nullptr; }
   // Tape slot of draw k: slot0 + k, or slot0 + rel[k] when the reference interleaves other draws.
   template <int K>
   __device__ __forceinline__ void normals_at(uint32_t site0, int slot0, const int (&rel)[K], T* out) const {
@@ -238,12 +243,12 @@ struct Rng {
 // and the owner lane then runs the reset arithmetic reading its column (TableRng below has the
 // draw interface of Rng).  Same sites, same words, same conversions as Rng -> same numbers.
 constexpr int kResetChunk = 8;
-constexpr int kResetRows = SITE_RESET_OBS2 + 7 - SITE_RESET;      // 31 site rows of 4 words
+constexpr int kResetRows = SITE_RESET_OBS2 + 6 - SITE_RESET;      // 30 site rows of 4 words
 
 __host__ __device__ constexpr bool reset_site_is_normal(uint32_t site) {
   return (site >= SITE_RESET + 4 && site <= SITE_RESET + 6) ||
-         (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 4) ||
-         (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 4);
+         (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 3) ||
+         (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 3);
 }
 // is `site` drawn by a reset of this flavour?  (superset over the run-time switches)
 __host__ __device__ constexpr bool reset_site_used(uint32_t site, int task, bool bullet, bool noise) {
@@ -253,9 +258,17 @@ __host__ __device__ constexpr bool reset_site_used(uint32_t site, int task, bool
     return k <= 5 || bullet;
   }
   if (site >= SITE_DR && site <= SITE_DR + 3) return site - SITE_DR <= 1 || bullet;
-  if (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 6) return noise;
-  if (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 6) return noise;
+  if (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 5) return noise;
+  if (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 5) return noise;
   return false;
+}
+// compact list of the site rows a reset of this flavour draws (row = site - SITE_RESET)
+struct ResetSiteList { int n; unsigned char row[kResetRows]; };
+__host__ __device__ constexpr ResetSiteList make_reset_sites(int task, bool bullet, bool noise) {
+  ResetSiteList l{};
+  for (int r = 0; r < kResetRows; ++r)
+    if (reset_site_used(SITE_RESET + (uint32_t)r, task, bullet, noise)) l.row[l.n++] = (unsigned char)r;
+  return l;
 }
 
 template <class T>
@@ -270,6 +283,9 @@ struct TableRng {
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] = tab[(r0 + k) * kResetChunk];
   }
+  template <int K> __device__ __forceinline__ void gen_normals(uint32_t s0, T* out) const { fetch<K>(s0, out); }
+  template <int K> __device__ __forceinline__ void gen_uniforms(uint32_t s0, T* out) const { fetch<K>(s0, out); }
+  __device__ __forceinline__ bool exact_draws() const { return false; }
   template <int K> __device__ __forceinline__ void normals_at(uint32_t s0, int, const int (&)[K], T* out) const { fetch<K>(s0, out); }
   template <int K> __device__ __forceinline__ void uniforms_at(uint32_t s0, int, const int (&)[K], T* out) const { fetch<K>(s0, out); }
   template <int K> __device__ __forceinline__ void normals(uint32_t s0, int, T* out) const { fetch<K>(s0, out); }

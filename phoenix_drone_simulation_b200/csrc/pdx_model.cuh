@@ -29,7 +29,7 @@ struct DevCfg {
   int slots_obs_full, slots_obs_gyro, slots_reset_task, slots_reset_dr, slots_step, slots_reset;
   T dr, time_step, mass, inertia[3], arm, gravity, thrust2weight, max_thrust,
       k_mass_dr, ftf1, hover_x, hover_action, motor_tc, ou_theta, ou_sigma, lpf_ratio,
-      pos_std, pos_unif, vel_std, quat_std, quat_unif, gyro_pi, gyro_sigma_b, gyro_rw, gyro_to,
+      pos_std, pos_unif, vel_std, quat_std, quat_unif, gyro_pi, gyro_sigma_b, gyro_rw, gyro_to, gyro_white,
       pen_action, pen_angle, pen_spin, pen_terminal, pen_velocity, arp, target[3], init_xyz[3],
       drag[3], prop_xy[4][2], prop_z, gec, prop_r, ge_hclip, lin_damp, ang_damp, ground_z;
 };
@@ -313,19 +313,55 @@ struct Model {
     }
   }
 
+  // Production draws: the two independent white-noise terms of the gyro model
+  // (0.0105 N + 5deg N, sensors.py:130-131) are one normal with the combined standard deviation
+  // gyro_white = sqrt(rw^2 + to^2) -- the same distribution with one draw instead of two.
+  __device__ __forceinline__ void gyro_update_merged(const T nb[3], const T nw[3], const T om[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      T& b = w[L.gyro_bias + k];
+      b = c.gyro_pi * b + c.gyro_sigma_b * nb[k];
+      const T noisy = (om[k] + b) + c.gyro_white * nw[k];
+      T& lp = w[L.gyro_lpf + k];
+      lp = (T(1) - c.lpf_ratio) * lp + (T(1) * c.lpf_ratio) * noisy;
+    }
+  }
+  // ... and what the oracle has to be told when it replays a launch (pdx_dump_draws): two
+  // reference draws N2, N3 with rw N2 + to N3 == gyro_white * nw.
+  template <class RG>
+  __device__ __forceinline__ void dump_gyro(const RG& rng, int slot, const T nb[3], const T nw[3]) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rng.dump_value(slot + k, (double)nb[k]);
+      rng.dump_value(slot + 3 + k, (double)nw[k] * (double)c.gyro_rw / (double)c.gyro_white);
+      rng.dump_value(slot + 6 + k, (double)nw[k] * (double)c.gyro_to / (double)c.gyro_white);
+    }
+  }
+
   // One physics sub-step plus the (discarded) observation call that follows it in the reference
   // (base.py:461-464): the OU draw and the gyro draws of that call come from one draw block.
   // `slot`: first tape slot of the sub-step; `full`: the observation call is a full one.
   __device__ __forceinline__ void substep(const Rng<T, RNG>& rng, const float a[4], int s, int slot, bool full) {
     if constexpr (NOISE) {
       const int g0 = 4 + (full ? 12 : 0);
-      const int rel[13] = {0, 1, 2, 3, g0, g0 + 1, g0 + 2, g0 + 3, g0 + 4, g0 + 5, g0 + 6, g0 + 7, g0 + 8};
-      T z[13];
-      rng.template normals_at<13>(SITE_SUBSTEP + 8 * s, slot, rel, z);
-      if constexpr (BULLET) physics_bullet(z, a); else physics_simple(z, a);
       T om[3];
-      body_rates(om);
-      gyro_update(&z[4], om);
+      if (rng.exact_draws()) {
+        const int rel[13] = {0, 1, 2, 3, g0, g0 + 1, g0 + 2, g0 + 3, g0 + 4, g0 + 5, g0 + 6, g0 + 7, g0 + 8};
+        T z[13];
+        rng.template normals_at<13>(SITE_SUBSTEP + 8 * s, slot, rel, z);
+        if constexpr (BULLET) physics_bullet(z, a); else physics_simple(z, a);
+        body_rates(om);
+        gyro_update(&z[4], om);
+      } else {
+        T z[10];
+        rng.template gen_normals<10>(SITE_SUBSTEP + 8 * s, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rng.dump_value(slot + k, (double)z[k]);
+        dump_gyro(rng, slot + g0, &z[4], &z[7]);
+        if constexpr (BULLET) physics_bullet(z, a); else physics_simple(z, a);
+        body_rates(om);
+        gyro_update_merged(&z[4], &z[7], om);
+      }
     } else {
       T z[4];
       rng.template normals<4>(SITE_SUBSTEP + 8 * s, slot, z);
@@ -347,20 +383,38 @@ struct Model {
     if constexpr (NOISE) {
       // tape slots of one call (sensors.py:84-118): 0-2 pos n, 3-5 pos u, 6-8 vel n, 9-11 vel u
       // (zero range, unused), 12-20 gyro n, 21-23 theta n, 24-26 theta u, 27-32 accelerometer.
-      const int reln[18] = {0, 1, 2, 6, 7, 8, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
-      const int relu[6] = {3, 4, 5, 24, 25, 26};
-      T zn[18], zu[6], e[3], q[4];
-      rng.template normals_at<18>(site0, slot, reln, zn);
-      rng.template uniforms_at<6>(site0 + 5, slot, relu, zu);
-      gyro_update(&zn[6], om);
+      T pn[3], vn[3], tn[3], zu[6], e[3], q[4];
+      if (rng.exact_draws()) {
+        const int reln[18] = {0, 1, 2, 6, 7, 8, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
+        const int relu[6] = {3, 4, 5, 24, 25, 26};
+        T zn[18];
+        rng.template normals_at<18>(site0, slot, reln, zn);
+        rng.template uniforms_at<6>(site0 + 4, slot, relu, zu);
+        gyro_update(&zn[6], om);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { pn[k] = zn[k]; vn[k] = zn[3 + k]; tn[k] = zn[15 + k]; }
+      } else {
+        T zn[15];
+        rng.template gen_normals<15>(site0, zn);
+        rng.template gen_uniforms<6>(site0 + 4, zu);
+        gyro_update_merged(&zn[6], &zn[9], om);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          pn[k] = zn[k]; vn[k] = zn[3 + k]; tn[k] = zn[12 + k];
+          rng.dump_value(slot + k, (double)pn[k]); rng.dump_value(slot + 3 + k, (double)zu[k]);
+          rng.dump_value(slot + 6 + k, (double)vn[k]); rng.dump_value(slot + 21 + k, (double)tn[k]);
+          rng.dump_value(slot + 24 + k, (double)zu[3 + k]);
+        }
+        dump_gyro(rng, slot + 12, &zn[6], &zn[9]);
+      }
       euler(e);
       const T pi = T(3.14159265358979323846);
       const T lo[3] = {-pi, -pi / T(2), -pi}, hi[3] = {pi, pi / T(2), pi};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        px[k] = p[k] + (c.pos_std * zn[k] + (-c.pos_unif + (c.pos_unif - (-c.pos_unif)) * zu[k]));
-        core[7 + k] = v[k] + c.vel_std * zn[3 + k];
-        const T th = c.quat_std * zn[15 + k] + (-c.quat_unif + (c.quat_unif - (-c.quat_unif)) * zu[3 + k]);
+        px[k] = p[k] + (c.pos_std * pn[k] + (-c.pos_unif + (c.pos_unif - (-c.pos_unif)) * zu[k]));
+        core[7 + k] = v[k] + c.vel_std * vn[k];
+        const T th = c.quat_std * tn[k] + (-c.quat_unif + (c.quat_unif - (-c.quat_unif)) * zu[3 + k]);
         e[k] = clampT(e[k] + th, lo[k], hi[k]);
         core[10 + k] = w[L.gyro_lpf + k];
       }
