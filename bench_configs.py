@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Throughput of the other BASELINE.json configurations (configs[2..4]) on ONE GPU -- companion of
+bench.py (which measures configs[1], the headline).  Prints one JSON line per configuration;
+the lines committed under profiles/ come from this script run under gpurun.
+
+    python bench_configs.py [--scale 1.0] [--steps 20] [--warmup 3]
+
+configs[2]  DroneCircleSimpleEnv-v0, 524,288 envs per GPU (4 Mi over 8 GPUs), H = 2 and H = 8
+configs[3]  DroneTakeOffSimpleEnv-v0, 1 Mi envs, ground effect on, obs noise, auto-reset (time limit
+            and non-finite guard), bounded actions a = -0.1 + 0.1 N(0,1)
+configs[4]  DroneHoverBulletEnv-v0 driving a PPO rollout (reference networks: pi 50-50 relu,
+            v 64-64 tanh) with the device-side collector: policy forward, env.step, buffer
+            writes, GAE and statistics, 131,072 envs x 64 steps per rollout
+"""
+import argparse
+import json
+import time
+
+import torch
+
+from phoenix_drone_simulation_b200 import VecEnv
+from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
+
+
+def open_loop(env_id, n, inner, steps, warmup, action_fn, **kw):
+    env = VecEnv(env_id, n, seed=1, **kw)
+    env.reset()
+    dev, d = env.device, env.obs_dim
+    g = torch.Generator(device=dev).manual_seed(0)
+    acts = action_fn((2, inner, n, 4), dev, g)
+    out = [{'obs': torch.empty((inner, n, d), device=dev), 'reward': torch.empty((inner, n), device=dev),
+            'cost': torch.empty((inner, n), device=dev),
+            'terminated': torch.empty((inner, n), dtype=torch.uint8, device=dev),
+            'truncated': torch.empty((inner, n), dtype=torch.uint8, device=dev)} for _ in range(2)]
+    for k in range(warmup):
+        env.step_many(acts[k & 1], out[k & 1])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        env.step_many(acts[k & 1], out[k & 1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    nonfinite = int((~torch.isfinite(out[0]['obs'])).sum()) + int((~torch.isfinite(out[0]['reward'])).sum())
+    s = env.episode_stats().cpu().tolist()
+    bytes_per = env.rollout_bytes(inner) / inner
+    v = steps * inner * n / (ms * 1e-3)
+    return {'env_id': env_id, 'envs': n, 'obs_dim': d, 'kwargs': {k: (v2 if not isinstance(v2, bool) else int(v2)) for k, v2 in kw.items()},
+            'env_steps_per_s': v, 'ms_per_launch': ms / steps, 'env_steps_per_launch': inner * n,
+            'algorithmic_bytes_per_env_step': bytes_per, 'algorithmic_GBps': v * bytes_per / 1e9,
+            'nonfinite_words_in_last_segment': nonfinite, 'episodes_finished': int(s[0]), 'mean_episode_length': (s[3] / s[0]) if s[0] else None}
+
+
+def uniform_actions(shape, dev, g):
+    return torch.rand(shape, device=dev, generator=g) * 2 - 1
+
+
+def takeoff_actions(shape, dev, g):
+    return -0.1 + 0.1 * torch.randn(shape, device=dev, generator=g)
+
+
+def ppo_rollout(n, T, rollouts, warmup):
+    torch.manual_seed(0)
+    env = VecEnv('DroneHoverBulletEnv-v0', n, seed=2, keep_final_obs=True)
+    ac = ActorCritic(env.obs_dim, device=env.device)
+    col = RolloutCollector(env, ac, T)
+    for _ in range(warmup):
+        data = col.collect()
+        col.update_running_statistics(data)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rollouts):
+        data = col.collect()
+        col.update_running_statistics(data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    wall = time.perf_counter() - t0
+    es = data['episode_stats']
+    return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'rollout_steps': T, 'what': 'PPO rollout: policy+value forward '
+            '(torch/cuBLAS), fused env.step kernel writing into [T,N,.] buffers, GAE kernel, running-stat moments',
+            'env_steps_per_s': rollouts * T * n / (ms * 1e-3), 'ms_per_rollout': ms / rollouts, 'wall_s': wall,
+            'episodes_in_last_rollout': es.n, 'ep_ret_mean': es.ret_mean, 'ep_len_mean': es.len_mean}
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument('--scale', type=float, default=1.0, help='scale the env counts (smoke runs)')
+    p.add_argument('--steps', type=int, default=20)
+    p.add_argument('--warmup', type=int, default=3)
+    a = p.parse_args()
+    sc = lambda n: max(1024, int(n * a.scale) // 128 * 128)
+    emit = lambda ln: print(json.dumps(ln), flush=True)
+    emit(dict(config='configs[2] H=2', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 16, a.steps, a.warmup, uniform_actions)))
+    emit(dict(config='configs[2] H=8', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 8, a.steps, a.warmup, uniform_actions,
+                                                  observation_history_size=8)))
+    emit(dict(config='configs[3]', **open_loop('DroneTakeOffSimpleEnv-v0', sc(1048576), 8, a.steps, a.warmup, takeoff_actions,
+                                              use_ground_effect=True, reset_on_nonfinite=True)))
+    emit(dict(config='configs[1] fixed policy', **open_loop('DroneHoverSimpleEnv-v0', sc(65536), 64, a.steps * 4, a.warmup,
+                                                           lambda s, d, g: -0.1111 + 0.05 * torch.randn(s, device=d, generator=g))))
+    emit(dict(config='configs[4]', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1)))
+
+
+if __name__ == '__main__':
+    main()

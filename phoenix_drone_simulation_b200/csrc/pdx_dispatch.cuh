@@ -58,17 +58,34 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
   d.ground_z = (T)p.ground_z;
 }
 
-// Threads per block of k_rollout: as large as the shared-memory plan allows (<= 128 so that a
-// 65,536-env shard still spreads over all 148 SMs), never below one warp.
+// Launch shape of k_rollout: threads per block (<= 128 so that a 65,536-env shard still spreads
+// over all 148 SMs) and one or two observation tiles, chosen to maximise the warps resident per SM
+// under the shared-memory plan (the kernel is capped at 128 registers: 16 warps per SM at most);
+// ties go to double buffering, then to the larger block.
+struct LaunchShape { int block, tiles; size_t smem; };
 template <class T>
-static int pick_block(int D, int NW, int C) {
-  int block = 128;
+static LaunchShape pick_shape(int D) {
+  int forced = 0;
   if (const char* e = getenv("PDX_BLOCK")) {          // tuning hook: 32 / 64 / 128 / 256
     const int b = atoi(e);
-    if (b == 32 || b == 64 || b == 128 || b == 256) block = b;
+    if (b == 32 || b == 64 || b == 128 || b == 256) forced = b;
   }
-  while (block > 32 && rollout_smem_bytes<T>(block, D) > (size_t)200 * 1024) block >>= 1;
-  return block;
+  LaunchShape best{0, 0, 0};
+  int best_warps = -1;
+  const int blocks[3] = {128, 64, 32};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int block = forced ? forced : blocks[bi];
+    for (int tiles = 2; tiles >= 1; --tiles) {
+      const size_t smem = rollout_smem_bytes<T>(block, D, tiles);
+      if (smem > (size_t)227 * 1024) continue;
+      const int by_smem = (int)(((size_t)228 * 1024) / (smem + 1024));
+      const int by_regs = 65536 / (128 * block);
+      const int warps = (by_smem < by_regs ? by_smem : by_regs) * (block / 32);
+      if (warps > best_warps) { best_warps = warps; best = LaunchShape{block, tiles, smem}; }
+    }
+    if (forced) break;
+  }
+  return best;
 }
 
 template <class T, int TASK, int PHYS, bool NOISE, int RNG>
@@ -82,9 +99,12 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     else k_reset<T, TASK, PHYS, NOISE, RNG><<<grid, block, 0, st>>>(ka);
     return cudaGetLastError();
   }
-  const int block = pick_block<T>(ka.c.obs_dim, Mo::NW, Mo::C);
-  const size_t smem = rollout_smem_bytes<T>(block, ka.c.obs_dim);
-  if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
+  const LaunchShape shape = pick_shape<T>(ka.c.obs_dim);
+  if (shape.block == 0) return cudaErrorInvalidConfiguration;
+  const int block = shape.block;
+  const size_t smem = shape.smem;
+  KArgs<T> kb = ka;
+  kb.n_tiles = shape.tiles;
   static size_t smem_set[16] = {0};                 // per device: opt-in dynamic shared memory
   const int dev = ka.b.device & 15;
   if (smem > smem_set[dev]) {
@@ -94,7 +114,7 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     smem_set[dev] = smem;
   }
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  k_rollout<T, TASK, PHYS, NOISE, RNG><<<grid, block, smem, st>>>(ka);
+  k_rollout<T, TASK, PHYS, NOISE, RNG><<<grid, block, smem, st>>>(kb);
   return cudaGetLastError();
 }
 
@@ -117,6 +137,7 @@ static cudaError_t launch_tu(int kind, const LaunchArgs& la) {
   ka.actions = la.actions; ka.mask = la.mask; ka.seed = la.seed; ka.counter = la.counter;
   ka.dump_step = la.dump_step; ka.dump_reset = la.dump_reset; ka.dump_init = la.dump_init;
   ka.n_steps = la.n_steps;
+  ka.n_tiles = 2;
   const bool noise = la.cfg->observation_noise != 0;
   // pdx_dump_draws runs the TAPE-mode kernels with dump pointers set.
   const int rng = (la.dump_step || la.dump_reset || la.dump_init) ? PDX_RNG_TAPE : la.cfg->rng_mode;

@@ -30,6 +30,7 @@ struct KArgs {
   double* dump_reset;
   double* dump_init;
   int n_steps;
+  int n_tiles;      // 2: observation tiles double buffered; 1: one tile, shifted in place
 };
 
 template <class T, int RNG>
@@ -349,14 +350,15 @@ __device__ __forceinline__ void fence_async_smem() {
 
 // Shared-memory plan of k_rollout (dynamic shared memory):
 //   T tile0, tile1 [B][D]                     observation rows of the block, layout == global slice
+//                                             (tile1 only when n_tiles == 2)
 //   T rtab [B/32][kResetRows*4][kResetChunk]  per warp: reset draws of up to kResetChunk finished envs
 //   double acc_sum [4][B], T acc_ext [4][B]   per-thread episode statistics (n, sum ret, sum ret^2,
 //                                             sum len; min/max ret, min/max len), reduced once
 //   int tile_free                             last step whose bulk copy is known to have left its tile
 //   unsigned char fin_lane [B]                per warp: lanes that finished this step, in lane order
 template <class T>
-__host__ __device__ inline size_t rollout_smem_bytes(int block, int D) {
-  size_t bytes = ((size_t)2 * block * D + (size_t)(block / 32) * kResetRows * 4 * kResetChunk + (size_t)4 * block) * sizeof(T);
+__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_tiles) {
+  size_t bytes = ((size_t)n_tiles * block * D + (size_t)(block / 32) * kResetRows * 4 * kResetChunk + (size_t)4 * block) * sizeof(T);
   bytes = (bytes + 15) & ~(size_t)15;
   return bytes + sizeof(double) * 4 * block + 16 + kMaxBlock;
 }
@@ -380,10 +382,11 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile0 = reinterpret_cast<T*>(smem_raw);
-  T* tile1 = tile0 + (size_t)B * D;
-  T* rtab = tile1 + (size_t)B * D + (size_t)warp * (kResetRows * 4 * kResetChunk);
-  T* acc_ext = tile1 + (size_t)B * D + (size_t)(B >> 5) * (kResetRows * 4 * kResetChunk);
-  const size_t off = (((size_t)2 * B * D + (size_t)(B >> 5) * kResetRows * 4 * kResetChunk + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
+  const int NT = a.n_tiles;
+  T* tile1 = NT == 2 ? tile0 + (size_t)B * D : tile0;
+  T* rtab = tile0 + (size_t)NT * B * D + (size_t)warp * (kResetRows * 4 * kResetChunk);
+  T* acc_ext = tile0 + (size_t)NT * B * D + (size_t)(B >> 5) * (kResetRows * 4 * kResetChunk);
+  const size_t off = (((size_t)NT * B * D + (size_t)(B >> 5) * kResetRows * 4 * kResetChunk + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
   double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
   volatile int* s_tile_free = reinterpret_cast<volatile int*>(smem_raw + off + sizeof(double) * 4 * B);
   unsigned char* s_fin_lane = smem_raw + off + sizeof(double) * 4 * B + 16 + (warp << 5);
@@ -530,12 +533,51 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       if (a.b.episode_length) a.b.episode_length[tn_off + i] = fin ? ep_len_out : 0;
     }
 
-    // ---- the tile of this step was last read by the bulk copy of step t-2: thread 0 publishes
-    // the newest step whose copy has drained (it waits right after issuing each copy)
-    if (t >= 2) { while (*s_tile_free < t - 2) {} }
+    // ---- the tile of this step was last read by the bulk copy of step t - n_tiles: thread 0
+    // publishes the newest step whose copy has drained (it waits right after issuing each copy;
+    // with a single tile the rows are shifted in place, ascending, once the previous copy left)
+    if (t >= NT) { while (*s_tile_free < t - NT) {} }
 
-    if (valid) {
-      // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319)
+    // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319).
+    // The tile has the row-major layout of the output, so lane l's row starts at bank l*D mod 32:
+    // when D is a multiple of 16 a warp walking its rows in step hits few banks (D = 160: ONE
+    // bank).  Each lane then walks its row rotated by its lane id (bank l*(D+1) + k: conflict
+    // free); the new entry goes through a warp-private column-major staging buffer because
+    // registers cannot be indexed by the rotated position.
+    if ((D & 15) == 0) {                                   // >= 16-way conflicts in natural order
+      const int rot = lane;
+      if (valid) {
+        for (int j = 0; j < H - 1; ++j) {
+          const bool alias = latency && (j + n_ep <= H);
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            int kk = k + rot;
+            kk = kk >= E ? kk - E : kk;
+            kk = kk >= E ? kk - E : kk;
+            T v = to[(j + 1) * E + kk];
+            if (alias && kk >= C) v = kk == C ? actT[0] : kk == C + 1 ? actT[1] : kk == C + 2 ? actT[2] : actT[3];
+            tn[j * E + kk] = v;
+          }
+        }
+      }
+      static_assert(E * 32 <= kResetRows * 4 * kResetChunk, "staging buffer must fit the reset table");
+      T* stg = rtab;                                       // the reset table is idle at this point
+#pragma unroll
+      for (int k = 0; k < C; ++k) stg[k * 32 + lane] = core[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg[(C + k) * 32 + lane] = a_new[k];
+      __syncwarp();
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          int kk = k + rot;
+          kk = kk >= E ? kk - E : kk;
+          kk = kk >= E ? kk - E : kk;
+          tn[(H - 1) * E + kk] = stg[kk * 32 + lane];
+        }
+      }
+      __syncwarp();
+    } else if (valid) {                                    // other strides: at most 8-way (measured faster)
       for (int j = 0; j < H - 1; ++j) {
         const bool alias = latency && (j + n_ep <= H);
 #pragma unroll
@@ -575,7 +617,13 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       }
       const uint64_t ctr = a.counter + (uint64_t)t;
       T o1[C], o2[C], stale[3];
-      if (do_reset) m.body_rates(stale);
+      if (do_reset) {
+        m.body_rates(stale);
+        if (c.reset_on_nonfinite) {                        // extension: do not seed the next episode's
+#pragma unroll
+          for (int k = 0; k < 3; ++k) if (!M<T>::finite(stale[k])) stale[k] = T(0);   // low pass with inf / NaN
+        }
+      }
       if constexpr (RNG == PDX_RNG_PHILOX) {
         const int my_rank = __popc(ballot & ((1u << lane) - 1u));
         const int total = __popc(ballot);
@@ -646,13 +694,14 @@ __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
       __syncthreads();
       if (tid == 0) {
         bulk_store(gdst, tile, bytes);
-        bulk_wait_read<1>();          // the copy issued one step ago has finished reading its tile
-        *s_tile_free = t - 1;
+        if (NT == 2) { bulk_wait_read<1>(); *s_tile_free = t - 1; }   // the copy issued one step ago has drained
+        else { bulk_wait_read<0>(); *s_tile_free = t; }
       }
     } else {
       __syncthreads();
       for (int e = tid; e < rows * D; e += B) gdst[e] = tile[e];
-      if (tid == 0) *s_tile_free = t - 1;
+      __syncthreads();
+      if (tid == 0) *s_tile_free = t;
     }
   }
 

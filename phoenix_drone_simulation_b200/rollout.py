@@ -126,8 +126,10 @@ class OnlineMeanStd:
         _, s2 = self._moments(x, mean_new.double())
         batch_var = self._avg((s2 / rows).float())
         M2 = n_A * self.std ** 2 + n_B * batch_var + delta ** 2 * (n_A * n_B / n_AB)
-        self.mean, self.count = mean_new, n_AB
-        self.std = torch.sqrt(M2 / n_AB)
+        # in place: CUDA graphs of the policy forward hold these tensors
+        self.mean.copy_(mean_new)
+        self.count.copy_(n_AB)
+        self.std.copy_(torch.sqrt(M2 / n_AB))
 
     def state_dict(self):
         return {'mean': self.mean.clone(), 'std': self.std.clone(), 'count': self.count.clone()}
@@ -216,7 +218,8 @@ class RolloutCollector:
     reset_each_rollout=True is the reference's behaviour (the env is reset at the start of every
     roll_out and episodes never span epochs, iwpg.py:353,375); False lets episodes continue."""
 
-    def __init__(self, env, ac, steps, gamma=0.99, lam=0.95, reset_each_rollout=True, dist=None):
+    def __init__(self, env, ac, steps, gamma=0.99, lam=0.95, reset_each_rollout=True, dist=None,
+                 use_cuda_graphs=True):
         assert env.final_obs is not None, 'construct the VecEnv with keep_final_obs=True'
         self.env, self.ac, self.T, self.gamma, self.lam = env, ac, int(steps), gamma, lam
         self.reset_each_rollout, self.dist = reset_each_rollout, dist
@@ -233,6 +236,30 @@ class RolloutCollector:
         self._outs = [{'obs': self.obs[t + 1], 'reward': self.rew[t], 'cost': self.cost[t],
                        'terminated': self.term[t], 'truncated': self.trunc[t]} for t in range(T)]
         self._started = False
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = None
+
+    def _policy_step(self, t, generator=None):
+        a, v, logp = self.ac.step(self.obs[t], generator)
+        self.act[t], self.val[t], self.logp[t] = a, v, logp
+
+    def _capture(self):
+        """One CUDA graph per step index: obs[t] -> act[t], val[t], logp[t] (normalise, two MLPs,
+        sample, log-prob: ~25 small kernels collapse into one graph launch)."""
+        cur = torch.cuda.current_stream(self.env.device)
+        side = torch.cuda.Stream(self.env.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._policy_step(0)
+        cur.wait_stream(side)
+        self._graphs, pool = [], None
+        for t in range(self.T):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._policy_step(t)
+            pool = pool or g.pool()
+            self._graphs.append(g)
 
     def collect(self, generator=None):
         env, ac, T = self.env, self.ac, self.T
@@ -244,9 +271,14 @@ class RolloutCollector:
         env.clear_episode_stats()
         self.boot.zero_()
         limit = env.max_episode_steps
+        graphs = self.use_cuda_graphs and generator is None
+        if graphs and self._graphs is None:
+            self._capture()
         for t in range(T):
-            a, v, logp = ac.step(self.obs[t], generator)
-            self.act[t], self.val[t], self.logp[t] = a, v, logp
+            if graphs:
+                self._graphs[t].replay()
+            else:
+                self._policy_step(t, generator)
             env.step(self.act[t], out=self._outs[t])
             # time-limit truncation needs V(last observation of the episode); the engine only
             # truncates when an episode reaches max_episode_steps, i.e. not before step `limit`
