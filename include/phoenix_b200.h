@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PDX_ABI_VERSION 4
+#define PDX_ABI_VERSION 5
 
 typedef enum PdxStatus {
   PDX_OK = 0,
@@ -50,6 +50,7 @@ enum { PDX_TASK_HOVER = 0, PDX_TASK_CIRCLE = 1, PDX_TASK_TAKEOFF = 2 };   /* env
 enum { PDX_PHYSICS_SIMPLE = 0, PDX_PHYSICS_BULLET = 1 };                  /* envs/physics.py:127 / :79 */
 enum { PDX_DTYPE_F32 = 0, PDX_DTYPE_F64 = 1 };
 enum { PDX_RNG_PHILOX = 0, PDX_RNG_TAPE = 1 };
+enum { PDX_CTRL_PWM = 0, PDX_CTRL_ATTITUDE_RATE = 1, PDX_CTRL_ATTITUDE = 2 };         /* envs/control.py:91,120,194 */
 enum { PDX_MAX_HISTORY = 16 };
 
 /* Persistent per-environment state lives in `state` as 16-byte "quads" (4 x real), one
@@ -77,7 +78,8 @@ typedef struct PdxConfig {
   int32_t obs_dim;              /* D = H * (C + 4)                     (base.py:143)      */
   int32_t reset_on_nonfinite;   /* extension: treat a non-finite state as truncation      */
   int32_t auto_reset;           /* 1: an env whose episode ends is reset inside pdx_step  */
-  int32_t reserved_i[2];
+  int32_t control_mode;         /* PDX_CTRL_*  (control_mode string, agents.py:71-78)       */
+  int32_t reserved_i[1];
   /* ---- scalars (all double; converted once per launch) --------------------------- */
   double domain_randomization;  /* p of U(v(1-p), v(1+p)); <= 0 disables (base.py:259)    */
   double time_step;             /* TIME_STEP = 1/sim_freq              (base.py:98)       */
@@ -141,7 +143,7 @@ int         pdx_config_finalize(PdxConfig* cfg);
 int         pdx_state_quads(const PdxConfig* cfg);       /* planes of 4 reals per env */
 /* Location of a named state field ("xyz","vel","rpy","omega","quat","omega_world","dt",
  * "mass","inertia","ftf1","motor_a","motor_k","motor_x","ring","ring_idx","ou",
- * "gyro_bias","gyro_lpf","last_action","ep_return","ep_length","ref_offset","hist").  Writes the first word index (quad*4+lane) and the
+ * "gyro_bias","gyro_lpf","last_action","pid","ep_return","ep_length","ref_offset","hist").  Writes the first word index (quad*4+lane) and the
  * length in words; returns 0, or PDX_ERR_INVALID if the field does not exist. */
 int         pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int* n_words);
 int         pdx_tape_slots(const PdxConfig* cfg, int* reset_slots, int* step_slots, int* init_slots);

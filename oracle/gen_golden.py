@@ -95,6 +95,11 @@ def make_actions(kind, T, hover_action, seed):
         return a
     if kind == 'takeoff':
         return (-0.1 + 0.1 * rng.standard_normal((T, 4))).astype(np.float32)
+    if kind == 'pid':         # thrust command near hover, small rate / angle commands, some outliers
+        a = (0.3 * rng.standard_normal((T, 4))).astype(np.float32)
+        a[:, 0] = (hover_action + 0.2 * rng.standard_normal(T)).astype(np.float32)
+        a[::17] = rng.uniform(-1.3, 1.3, (len(a[::17]), 4)).astype(np.float32)
+        return a
     raise ValueError(kind)
 
 
@@ -193,6 +198,13 @@ CASES = [
     ('hover_bullet_h3', 'DroneHoverBulletEnv-v0', dict(observation_history_size=3), 'mixed', 150, 43),
     ('circle_bullet_default', 'DroneCircleBulletEnv-v0', {}, 'mixed', 300, 51),
     ('takeoff_bullet_default', 'DroneTakeOffBulletEnv-v0', {}, 'takeoff', 300, 61),
+    # --- PID control modes (experiments/07 uses agg 4 / 8 with the Bullet ids) ---
+    ('hover_simple_attrate', 'DroneHoverSimpleEnv-v0', dict(control_mode='AttitudeRate'), 'pid', 300, 71),
+    ('hover_simple_attitude_det', 'DroneHoverSimpleEnv-v0', dict(DET, control_mode='Attitude'), 'pid', 300, 72),
+    ('circle_bullet_attrate_agg4', 'DroneCircleBulletEnv-v0',
+     dict(control_mode='AttitudeRate', aggregate_phy_steps=4), 'pid', 200, 73),
+    ('hover_bullet_attitude_agg8', 'DroneHoverBulletEnv-v0',
+     dict(control_mode='Attitude', aggregate_phy_steps=8), 'pid', 150, 74),
 ]
 
 

@@ -202,7 +202,7 @@ class OracleEnv:
                  observation_history_size=2, enable_reset_distribution=True,
                  aggregate_phy_steps=None, latency=0.015, motor_time_constant=0.080,
                  motor_thrust_noise=0.05, use_ground_effect=False,
-                 lin_damping=0.04, ang_damping=0.04, **penalties):
+                 lin_damping=0.04, ang_damping=0.04, control_mode='PWM', **penalties):
         self.task, self.physics = ENV_IDS[env_id]
         self.src = source if source is not None else NumpyGlobalSource()
         bullet = self.physics == 'bullet'
@@ -240,6 +240,20 @@ class OracleEnv:
         self.MOTOR_T = motor_time_constant
         self.ou_sigma = 0.2 * motor_thrust_noise                     # agents.py:206
         self.ou_theta = 0.15
+        # control.py:13-26,120-287: firmware PID gains; the controllers keep the NOMINAL time step
+        # under domain randomisation (agents.py:74-78, quirk A.6-13)
+        assert control_mode in ('PWM', 'AttitudeRate', 'Attitude')
+        self.control_mode = control_mode
+        self.rate_kp = np.array([250.0, 250.0, 120.0])
+        self.rate_ki = np.array([500.0, 500.0, 16.7])
+        self.rate_kd = np.array([2.5, 2.5, 0.0])
+        self.rate_lim = np.array([33.3, 33.3, 166.7])
+        self.att_kp = np.array([6.0, 6.0, 6.0])
+        self.att_ki = np.array([3.0, 3.0, 1.0])
+        self.att_kd = np.array([0.0, 0.0, 0.35])
+        self.att_lim = np.array([20.0, 20.0, 360.0])
+        self.rate_int, self.rate_err = np.zeros(3), np.zeros(3)
+        self.att_int, self.att_err = np.zeros(3), np.zeros(3)
 
         # sensors.py:18-33,121-128 (dt is the *nominal* 1/SIM_FREQ, hover.py:144)
         sdt = 1 / self.sim_freq
@@ -306,7 +320,49 @@ class OracleEnv:
         self.obs_dim = self.H * (self._observe().size + 4)
 
     # ----------------------------------------------------------------------------------------
-    #  motor model: agents.py:259-298, control.py:94-100, envs/utils.py:104-108
+    #  control.act: control.py:94-100 (PWM), :120-191 (AttitudeRate), :194-287 (Attitude)
+    # ----------------------------------------------------------------------------------------
+    def _rate_pid(self, rpy_dot_target):
+        dt = self.TIME_STEP
+        error = (rpy_dot_target - self.omega) * 180. / np.pi
+        derivative = (error - self.rate_err) / dt
+        self.rate_err = error
+        self.rate_int = self.rate_int + error * dt
+        self.rate_int = np.clip(self.rate_int, -self.rate_lim, self.rate_lim)
+        return self.rate_kp * error + self.rate_ki * self.rate_int + self.rate_kd * derivative
+
+    def _att_pid(self, rpy_target):
+        dt = self.TIME_STEP
+        error = (rpy_target - self.rpy) * 180. / np.pi
+        derivative = (error - self.att_err) / dt
+        self.att_err = error
+        self.att_int = self.att_int + error * dt
+        self.att_int = np.clip(self.att_int, -self.att_lim, self.att_lim)
+        offs = self.att_kp * error + self.att_ki * self.att_int + self.att_kd * derivative
+        return offs / 180. * np.pi
+
+    @staticmethod
+    def _mix(f, thrust):
+        """rpy_control_factors_to_PWM, control.py:34-50 (QUAD_FORMATION_X)."""
+        r, p, y = f[0] / 2.0, f[1] / 2.0, f[2]
+        return np.array([np.clip(thrust - r - p - y, 0, 60000), np.clip(thrust - r + p + y, 0, 60000),
+                         np.clip(thrust + r + p - y, 0, 60000), np.clip(thrust + r - p + y, 0, 60000)])
+
+    def _control(self, action):
+        """`action` keeps its dtype: float32 from the policy (Simple agent) or float64 out of the
+        latency ring -- the leading arithmetic of every mode runs in that dtype (quirk A.6-3)."""
+        clipped = np.clip(action, -1, 1)
+        if self.control_mode == 'PWM':
+            return 30000 + clipped * 30000
+        if self.control_mode == 'AttitudeRate':
+            thrust = 30000 + clipped[0] * 30000
+            return self._mix(self._rate_pid(clipped[1:4] * np.pi / 3), thrust)
+        thrust = 45000 + clipped[0] * 10000
+        rate_targets = self._att_pid(clipped[1:4] * np.pi / 18)
+        return self._mix(self._rate_pid(rate_targets), thrust)
+
+    # ----------------------------------------------------------------------------------------
+    #  motor model: agents.py:259-298, envs/utils.py:104-108
     # ----------------------------------------------------------------------------------------
     def _motor(self, action):
         self.drone_last_action = action.copy()
@@ -316,7 +372,7 @@ class OracleEnv:
             self.ring_idx = (self.ring_idx + 1) % self.buf_size
         else:
             delayed = action
-        pwm = 30000 + np.clip(delayed, -1, 1) * 30000          # float32 if action is float32
+        pwm = self._control(delayed)
         self.ou = self.ou + (self.ou_theta * (0 - self.ou) + self.ou_sigma * self.src.randn(4))
         u = pwm / 60000
         if self.use_motor_dynamics:
@@ -589,7 +645,9 @@ class OracleEnv:
         self.src.begin_reset(self.n_resets)
         self.n_resets += 1
         self.iteration = 0
-        # drone.reset(): agents.py:377-386
+        # drone.reset(): agents.py:377-386 (control.reset(): control.py:182-191,282-287)
+        self.rate_int, self.rate_err = np.zeros(3), np.zeros(3)
+        self.att_int, self.att_err = np.zeros(3), np.zeros(3)
         self.x = np.zeros(4)
         self.ring_idx = 0
         self.ring = np.zeros_like(self.ring)

@@ -20,6 +20,10 @@ UNITS = {
     'pdx_tu_f32_bullet.cu': ['-use_fast_math'],
     'pdx_tu_f64_simple.cu': ['-fmad=false'],
     'pdx_tu_f64_bullet.cu': ['-fmad=false'],
+    'pdx_tu_f32_simple_pid.cu': ['-use_fast_math'],
+    'pdx_tu_f32_bullet_pid.cu': ['-use_fast_math'],
+    'pdx_tu_f64_simple_pid.cu': ['-fmad=false'],
+    'pdx_tu_f64_bullet_pid.cu': ['-fmad=false'],
     'pdx_abi.cu': [],
     'pdx_rollout.cu': [],
 }
@@ -59,7 +63,7 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
         return r.stderr
 
-    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         logs = list(ex.map(run, jobs))
     objs = [os.path.join(obj_dir, u.replace('.cu', '.o')) for u in UNITS]
     if force or jobs or _stale(LIB, objs):

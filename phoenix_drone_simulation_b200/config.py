@@ -81,9 +81,8 @@ class EnvConfig:
     def __post_init__(self):
         if self.env_id not in ENV_IDS:
             raise KeyError(f'unknown env id {self.env_id!r}; known: {sorted(ENV_IDS)}')
-        if self.control_mode != 'PWM':
-            raise NotImplementedError('control_mode %r: only PWM is on the B200 path '
-                                      '(PID modes are SURVEY 8f "next")' % self.control_mode)
+        if self.control_mode not in _lib.PDX_CTRL:
+            raise NotImplementedError('control_mode %r: expected one of %s' % (self.control_mode, sorted(_lib.PDX_CTRL)))
         if self.render_mode not in (None, 'rgb_array'):
             raise NotImplementedError('rendering (PyBullet GUI) is not provided')
         self.task, self.physics, self.drone_model, self.sim_freq, default_agg = ENV_IDS[self.env_id]
@@ -103,6 +102,7 @@ class EnvConfig:
         c.physics = _lib.PDX_PHYSICS[self.physics]
         c.dtype = dtype_code
         c.rng_mode = rng_mode
+        c.control_mode = _lib.PDX_CTRL[self.control_mode]                      # agents.py:71-78
         c.observation_noise = 1 if self.observation_noise > 0 else 0
         c.history = int(self.observation_history_size)
         c.agg = int(self.aggregate_phy_steps)

@@ -20,7 +20,7 @@ int cuda_fail(cudaError_t e) {
 }
 
 pdx::Layout layout_of(const PdxConfig* c) {
-  return pdx::make_layout(c->task, c->physics, c->observation_noise != 0);
+  return pdx::make_layout(c->task, c->physics, c->observation_noise != 0, c->control_mode != PDX_CTRL_PWM);
 }
 
 int validate(const PdxConfig* c) {
@@ -29,6 +29,7 @@ int validate(const PdxConfig* c) {
   if (c->physics < 0 || c->physics > 1) return fail(PDX_ERR_INVALID, "bad physics");
   if (c->dtype < 0 || c->dtype > 1) return fail(PDX_ERR_INVALID, "bad dtype");
   if (c->rng_mode < 0 || c->rng_mode > 1) return fail(PDX_ERR_INVALID, "bad rng_mode");
+  if (c->control_mode < 0 || c->control_mode > 2) return fail(PDX_ERR_INVALID, "bad control_mode");
   if (c->history < 1 || c->history > PDX_MAX_HISTORY) return fail(PDX_ERR_INVALID, "observation_history_size must be in [1,16]");
   if (c->agg < 1 || c->agg > 8) return fail(PDX_ERR_INVALID, "aggregate_phy_steps must be in [1,8]");
   if (c->obs_rate < 1 || c->agg % c->obs_rate != 0)
@@ -78,10 +79,13 @@ int launch(int kind, const PdxConfig* cfg, const PdxBuffers* buf, const float* a
   e = cudaSetDevice(buf->device);       // this library carries its own (static) CUDA runtime
   if (e != cudaSuccess) return cuda_fail(e);
   pdx::LaunchArgs la{&c, buf, actions, mask, seed, counter, ds, dr, di, n_steps, (cudaStream_t)stream};
+  const bool pid = c.control_mode != PDX_CTRL_PWM, simple = c.physics == PDX_PHYSICS_SIMPLE;
   if (c.dtype == PDX_DTYPE_F32)
-    e = c.physics == PDX_PHYSICS_SIMPLE ? pdx::launch_f32_simple(kind, la) : pdx::launch_f32_bullet(kind, la);
+    e = simple ? (pid ? pdx::launch_f32_simple_pid(kind, la) : pdx::launch_f32_simple(kind, la))
+               : (pid ? pdx::launch_f32_bullet_pid(kind, la) : pdx::launch_f32_bullet(kind, la));
   else
-    e = c.physics == PDX_PHYSICS_SIMPLE ? pdx::launch_f64_simple(kind, la) : pdx::launch_f64_bullet(kind, la);
+    e = simple ? (pid ? pdx::launch_f64_simple_pid(kind, la) : pdx::launch_f64_simple(kind, la))
+               : (pid ? pdx::launch_f64_bullet_pid(kind, la) : pdx::launch_f64_bullet(kind, la));
   if (e != cudaSuccess) return cuda_fail(e);
   return PDX_OK;
 }
@@ -118,7 +122,7 @@ int pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int
       {"quat", L.quat, 4}, {"omega_world", L.omega_world, 3}, {"dt", L.dt, 1}, {"mass", L.mass, 1},
       {"inertia", L.inertia, 3}, {"ftf1", L.ftf1, 1}, {"motor_b", L.motor_b, 4},
       {"motor_k", L.motor_k, 4}, {"motor_x", L.motor_x, 4}, {"ring", L.ring, 8},
-      {"ring_idx", L.ring_idx, 1}, {"ou", L.ou, 4}, {"last_action", L.last_action, 4},
+      {"ring_idx", L.ring_idx, 1}, {"ou", L.ou, 4}, {"last_action", L.last_action, 4}, {"pid", L.pid, 12},
       {"ep_return", L.ep_return, 1}, {"ep_length", L.ep_length, 1},
       {"ref_offset", L.ref_offset, 1}, {"gyro_bias", L.gyro_bias, 3}, {"gyro_lpf", L.gyro_lpf, 3},
       {"hist", L.n_quads * 4, (cfg->history - 1) * L.hist_quads * 4},

@@ -30,6 +30,7 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
   d.buf_size = p.buf_size; d.use_motor_dynamics = p.use_motor_dynamics;
   d.reset_distribution = p.reset_distribution; d.ground_effect = p.ground_effect;
   d.max_episode_steps = p.max_episode_steps; d.core_dim = p.core_dim; d.obs_dim = p.obs_dim;
+  d.control_mode = p.control_mode;
   d.dr_on = p.domain_randomization > 0 ? 1 : 0; d.reset_on_nonfinite = p.reset_on_nonfinite; d.auto_reset = p.auto_reset;
   d.slots_obs_full = ts.obs_full; d.slots_obs_gyro = ts.obs_gyro;
   d.slots_reset_task = ts.reset_task; d.slots_reset_dr = ts.reset_dr;
@@ -88,15 +89,14 @@ static LaunchShape pick_shape(int D) {
   return best;
 }
 
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
 static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
-  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
   const int64_t n = ka.b.n_envs;
   if (kind != KIND_STEP) {
     const int block = 128;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    if (kind == KIND_INIT) k_init<T, TASK, PHYS, NOISE, RNG><<<grid, block, 0, st>>>(ka);
-    else k_reset<T, TASK, PHYS, NOISE, RNG><<<grid, block, 0, st>>>(ka);
+    if (kind == KIND_INIT) k_init<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, 0, st>>>(ka);
+    else k_reset<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, 0, st>>>(ka);
     return cudaGetLastError();
   }
   const LaunchShape shape = pick_shape<T>(ka.c.obs_dim);
@@ -108,28 +108,28 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
   static size_t smem_set[16] = {0};                 // per device: opt-in dynamic shared memory
   const int dev = ka.b.device & 15;
   if (smem > smem_set[dev]) {
-    const cudaError_t e = cudaFuncSetAttribute(k_rollout<T, TASK, PHYS, NOISE, RNG>,
+    const cudaError_t e = cudaFuncSetAttribute(k_rollout<T, TASK, PHYS, NOISE, RNG, PID>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set[dev] = smem;
   }
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  k_rollout<T, TASK, PHYS, NOISE, RNG><<<grid, block, smem, st>>>(kb);
+  k_rollout<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, smem, st>>>(kb);
   return cudaGetLastError();
 }
 
-template <class T, int TASK, int PHYS>
+template <class T, int TASK, int PHYS, bool PID>
 static cudaError_t launch_nr(int kind, bool noise, int rng, const KArgs<T>& ka, cudaStream_t st) {
   if (noise) {
-    if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, true, PDX_RNG_PHILOX>(kind, ka, st);
-    return launch_kind<T, TASK, PHYS, true, PDX_RNG_TAPE>(kind, ka, st);
+    if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, true, PDX_RNG_PHILOX, PID>(kind, ka, st);
+    return launch_kind<T, TASK, PHYS, true, PDX_RNG_TAPE, PID>(kind, ka, st);
   }
-  if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, false, PDX_RNG_PHILOX>(kind, ka, st);
-  return launch_kind<T, TASK, PHYS, false, PDX_RNG_TAPE>(kind, ka, st);
+  if (rng == PDX_RNG_PHILOX) return launch_kind<T, TASK, PHYS, false, PDX_RNG_PHILOX, PID>(kind, ka, st);
+  return launch_kind<T, TASK, PHYS, false, PDX_RNG_TAPE, PID>(kind, ka, st);
 }
 
-// One physics flavour per translation unit.
-template <class T, int PHYS>
+// One arithmetic type, physics flavour and control family per translation unit.
+template <class T, int PHYS, bool PID>
 static cudaError_t launch_tu(int kind, const LaunchArgs& la) {
   KArgs<T> ka;
   fill_devcfg<T>(*la.cfg, ka.c);
@@ -142,9 +142,9 @@ static cudaError_t launch_tu(int kind, const LaunchArgs& la) {
   // pdx_dump_draws runs the TAPE-mode kernels with dump pointers set.
   const int rng = (la.dump_step || la.dump_reset || la.dump_init) ? PDX_RNG_TAPE : la.cfg->rng_mode;
   switch (la.cfg->task) {
-    case PDX_TASK_HOVER: return launch_nr<T, PDX_TASK_HOVER, PHYS>(kind, noise, rng, ka, la.stream);
-    case PDX_TASK_CIRCLE: return launch_nr<T, PDX_TASK_CIRCLE, PHYS>(kind, noise, rng, ka, la.stream);
-    default: return launch_nr<T, PDX_TASK_TAKEOFF, PHYS>(kind, noise, rng, ka, la.stream);
+    case PDX_TASK_HOVER: return launch_nr<T, PDX_TASK_HOVER, PHYS, PID>(kind, noise, rng, ka, la.stream);
+    case PDX_TASK_CIRCLE: return launch_nr<T, PDX_TASK_CIRCLE, PHYS, PID>(kind, noise, rng, ka, la.stream);
+    default: return launch_nr<T, PDX_TASK_TAKEOFF, PHYS, PID>(kind, noise, rng, ka, la.stream);
   }
 }
 
@@ -153,5 +153,9 @@ cudaError_t launch_f32_simple(int kind, const LaunchArgs& la);
 cudaError_t launch_f32_bullet(int kind, const LaunchArgs& la);
 cudaError_t launch_f64_simple(int kind, const LaunchArgs& la);
 cudaError_t launch_f64_bullet(int kind, const LaunchArgs& la);
+cudaError_t launch_f32_simple_pid(int kind, const LaunchArgs& la);
+cudaError_t launch_f32_bullet_pid(int kind, const LaunchArgs& la);
+cudaError_t launch_f64_simple_pid(int kind, const LaunchArgs& la);
+cudaError_t launch_f64_bullet_pid(int kind, const LaunchArgs& la);
 
 }  // namespace pdx

@@ -59,10 +59,10 @@ template <class T> __device__ __forceinline__ T unif(T lo, T hi, T u) { return l
 //  Outputs: m.w (complete new state, OU words untouched), o1 / o2 = the two observation calls
 //  (base.py:420,429); the history is H-1 copies of (o1, last_action) and one (o2, last_action).
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG, class RG>
-__device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, const RG& rng,
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, class RG>
+__device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG, PID>& m, const RG& rng,
                                           const T stale[3], T* o1, T* o2) {
-  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   const DevCfg<T>& c = m.c;
   T* w = m.w;
@@ -210,6 +210,10 @@ __device__ __forceinline__ void reset_env(Model<T, TASK, PHYS, NOISE, RNG>& m, c
   for (int k = 0; k < 4; ++k) w[L.last_action + k] = la[k];
   w[L.ep_return] = T(0);
   w[L.ep_length] = T(0);
+  if constexpr (PID) {                                    // control.reset(): control.py:182-191,282-287
+#pragma unroll
+    for (int k = 0; k < 12; ++k) w[L.pid + k] = T(0);
+  }
 
   // two observation calls (base.py:420,429)
   T target[3] = {c.target[0], c.target[1], c.target[2]};
@@ -239,9 +243,9 @@ __device__ __forceinline__ void store_history(T* state, int64_t n, int64_t i, in
 // ---------------------------------------------------------------------------------------------
 //  constructor: zero state, nominal parameters, base.py:143's compute_observation()
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
 __global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
-  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   const int64_t n = a.b.n_envs;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,9 +284,9 @@ __global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
 // ---------------------------------------------------------------------------------------------
 //  explicit reset of all / masked environments (dense: one thread per env)
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
 __global__ void __launch_bounds__(kMaxBlock) k_reset(const KArgs<T> a) {
-  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
   const int64_t n = a.b.n_envs;
@@ -366,9 +370,9 @@ __host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_til
 // ---------------------------------------------------------------------------------------------
 //  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
 __global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
-  typedef Model<T, TASK, PHYS, NOISE, RNG> Mo;
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
   const DevCfg<T>& c = a.c;

@@ -18,6 +18,8 @@ struct Layout {
   int dt, mass, inertia, ftf1;
   int motor_b, motor_k, motor_x, ring, ring_idx;   // Bullet agent only
   int ou, last_action;
+  int pid;                 // PID control modes: rate integral 3, rate last error 3, attitude integral 3,
+                           // attitude last error 3 (control.py:133-134,226-227)
   int ep_return, ep_length;
   int ref_offset;          // circle only
   int gyro_bias, gyro_lpf; // noise only
@@ -36,7 +38,7 @@ constexpr int core_dim_of(int task, bool noise) {
   return task == PDX_TASK_HOVER ? (noise ? 13 : 17) : task == PDX_TASK_CIRCLE ? 16 : 20;
 }
 
-constexpr Layout make_layout(int task, int physics, bool noise) {
+constexpr Layout make_layout(int task, int physics, bool noise, bool pid = false) {
   Layout L{};
   int w = 0;
   auto take = [&w](int n) { int o = w; w += n; return o; };
@@ -59,6 +61,7 @@ constexpr Layout make_layout(int task, int physics, bool noise) {
   }
   L.ou = take(4);
   L.last_action = take(4);
+  L.pid = pid ? take(12) : -1;
   L.ep_return = take(1);
   L.ep_length = take(1);
   L.gyro_bias = L.gyro_lpf = -1;

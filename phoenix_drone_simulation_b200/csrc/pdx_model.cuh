@@ -24,7 +24,7 @@ namespace pdx {
 // Device-side copy of PdxConfig in the arithmetic type (built once per launch on the host).
 template <class T>
 struct DevCfg {
-  int history, agg, obs_rate, use_latency, buf_size, use_motor_dynamics, reset_distribution,
+  int control_mode, history, agg, obs_rate, use_latency, buf_size, use_motor_dynamics, reset_distribution,
       ground_effect, max_episode_steps, core_dim, obs_dim, dr_on, reset_on_nonfinite, auto_reset;
   int slots_obs_full, slots_obs_gyro, slots_reset_task, slots_reset_dr, slots_step, slots_reset;
   T dr, time_step, mass, inertia[3], arm, gravity, thrust2weight, max_thrust,
@@ -69,9 +69,9 @@ template <class T> __device__ __forceinline__ T norm3(T a, T b, T c) {
   return M<T>::sqrt(a * a + b * b + c * c);
 }
 
-template <class T, int TASK, int PHYS, bool NOISE, int RNG>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID = false>
 struct Model {
-  static constexpr Layout L = make_layout(TASK, PHYS, NOISE);
+  static constexpr Layout L = make_layout(TASK, PHYS, NOISE, PID);
   static constexpr int NW = L.n_quads * 4;
   static constexpr int C = L.core_dim;
   static constexpr int E = C + 4;              // one history entry: observation + action
@@ -133,29 +133,88 @@ struct Model {
   __device__ __forceinline__ void motor(const T z[4], const float a[4], T f[4], T* tz) {
     T u[4];
     bool delayed = false;
+    T d[4];                                      // action the controller sees, in T
     if constexpr (BULLET) {
       if (c.use_latency) {
         // agents.py:267-276: delayed action out of the ring, current action in.  The ring is
-        // float64 in the reference, so the PWM stage runs in T here (quirk A.6-3).
+        // float64 in the reference, so the control stage runs in T here (quirk A.6-3).
         delayed = true;
         const int idx = (int)w[L.ring_idx];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const T d = idx == 0 ? w[L.ring + k] : w[L.ring + 4 + k];
+          d[k] = idx == 0 ? w[L.ring + k] : w[L.ring + 4 + k];
           if (idx == 0) w[L.ring + k] = (T)a[k]; else w[L.ring + 4 + k] = (T)a[k];
-          const T pwm = T(30000) + clampT(d, T(-1), T(1)) * T(30000);
-          u[k] = pwm / T(60000);
         }
         w[L.ring_idx] = (T)((idx + 1) % c.buf_size);
       }
     }
-    if (!delayed) {
-      // control.py:98-99 evaluated in float32 because the policy's action is float32.
+    if constexpr (!PID) {
+      if (delayed) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float pwm = 30000.0f + fminf(fmaxf(a[k], -1.0f), 1.0f) * 30000.0f;
-        u[k] = (T)(pwm / 60000.0f);
+        for (int k = 0; k < 4; ++k) {
+          const T pwm = T(30000) + clampT(d[k], T(-1), T(1)) * T(30000);
+          u[k] = pwm / T(60000);
+        }
+      } else {
+        // control.py:98-99 evaluated in float32 because the policy's action is float32.
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float pwm = 30000.0f + fminf(fmaxf(a[k], -1.0f), 1.0f) * 30000.0f;
+          u[k] = (T)(pwm / 60000.0f);
+        }
       }
+    } else {
+      // control.py:120-287.  Leading arithmetic (clip, thrust, targets) in the dtype of the action
+      // the controller receives: T out of the latency ring, float32 straight from the policy.
+      const T pi = T(3.14159265358979323846);
+      const bool attitude = c.control_mode == PDX_CTRL_ATTITUDE;
+      T thrust, tgt[3];
+      if (delayed) {
+        const T c0 = clampT(d[0], T(-1), T(1));
+        thrust = attitude ? T(45000) + c0 * T(10000) : T(30000) + c0 * T(30000);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tgt[k] = (clampT(d[1 + k], T(-1), T(1)) * pi) / (attitude ? T(18) : T(3));
+      } else {
+        const float c0 = fminf(fmaxf(a[0], -1.0f), 1.0f);
+        thrust = (T)(attitude ? 45000.0f + c0 * 10000.0f : 30000.0f + c0 * 30000.0f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          tgt[k] = (T)((fminf(fmaxf(a[1 + k], -1.0f), 1.0f) * 3.14159265358979323846f) / (attitude ? 18.0f : 3.0f));
+      }
+      const T dt = c.time_step;                  // controllers keep the nominal step (quirk A.6-13)
+      if (attitude) {                            // outer loop: control.py:264-280
+        const T kp[3] = {T(6), T(6), T(6)}, ki[3] = {T(3), T(3), T(1)}, kd[3] = {T(0), T(0), T(0.35)};
+        const T lim[3] = {T(20), T(20), T(360)};
+        T e[3];
+        euler(e);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const T err = ((tgt[k] - e[k]) * T(180)) / pi;
+          const T der = (err - w[L.pid + 9 + k]) / dt;
+          w[L.pid + 9 + k] = err;
+          w[L.pid + 6 + k] = clampT(w[L.pid + 6 + k] + err * dt, -lim[k], lim[k]);
+          const T offs = (kp[k] * err + ki[k] * w[L.pid + 6 + k]) + kd[k] * der;
+          tgt[k] = (offs / T(180)) * pi;
+        }
+      }
+      // rate loop: control.py:160-180, firmware gains control.py:13-26
+      const T kp[3] = {T(250), T(250), T(120)}, ki[3] = {T(500), T(500), T(16.7)}, kd[3] = {T(2.5), T(2.5), T(0)};
+      const T lim[3] = {T(33.3), T(33.3), T(166.7)};
+      T om[3], f[3];
+      body_rates(om);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const T err = ((tgt[k] - om[k]) * T(180)) / pi;
+        const T der = (err - w[L.pid + 3 + k]) / dt;
+        w[L.pid + 3 + k] = err;
+        w[L.pid + k] = clampT(w[L.pid + k] + err * dt, -lim[k], lim[k]);
+        f[k] = (kp[k] * err + ki[k] * w[L.pid + k]) + kd[k] * der;
+      }
+      // mixer: control.py:34-50 (QUAD_FORMATION_X)
+      const T r = f[0] / T(2), p = f[1] / T(2), y = f[2];
+      const T pw[4] = {((thrust - r) - p) - y, ((thrust - r) + p) + y, ((thrust + r) + p) - y, ((thrust + r) - p) + y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = clampT(pw[k], T(0), T(60000)) / T(60000);
     }
     T tq[4];
 #pragma unroll

@@ -1,5 +1,5 @@
-// Instantiates the double kernels of the bullet physics flavour (see pdx_dispatch.cuh).
+// Instantiates the double kernels of the bullet physics flavour, PWM control (see pdx_dispatch.cuh).
 #include "pdx_dispatch.cuh"
 namespace pdx {
-cudaError_t launch_f64_bullet(int kind, const LaunchArgs& la) { return launch_tu<double, PDX_PHYSICS_BULLET>(kind, la); }
+cudaError_t launch_f64_bullet(int kind, const LaunchArgs& la) { return launch_tu<double, PDX_PHYSICS_BULLET, false>(kind, la); }
 }  // namespace pdx

@@ -9,12 +9,13 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 PDX_TASK = {'hover': 0, 'circle': 1, 'takeoff': 2}
 PDX_PHYSICS = {'SimplePhysics': 0, 'PyBulletPhysics': 1}
 PDX_DTYPE_F32, PDX_DTYPE_F64 = 0, 1
 PDX_RNG_PHILOX, PDX_RNG_TAPE = 0, 1
+PDX_CTRL = {'PWM': 0, 'AttitudeRate': 1, 'Attitude': 2}
 
 
 class PhoenixB200Error(RuntimeError):
@@ -28,7 +29,8 @@ class PdxConfig(C.Structure):
         ('obs_rate', C.c_int32), ('use_latency', C.c_int32), ('buf_size', C.c_int32),
         ('use_motor_dynamics', C.c_int32), ('reset_distribution', C.c_int32),
         ('ground_effect', C.c_int32), ('max_episode_steps', C.c_int32), ('core_dim', C.c_int32),
-        ('obs_dim', C.c_int32), ('reset_on_nonfinite', C.c_int32), ('auto_reset', C.c_int32), ('reserved_i', C.c_int32 * 2),
+        ('obs_dim', C.c_int32), ('reset_on_nonfinite', C.c_int32), ('auto_reset', C.c_int32), ('control_mode', C.c_int32),
+        ('reserved_i', C.c_int32 * 1),
         ('domain_randomization', C.c_double), ('time_step', C.c_double), ('sensor_dt', C.c_double),
         ('mass', C.c_double), ('inertia', C.c_double * 3), ('arm', C.c_double),
         ('gravity', C.c_double), ('thrust2weight', C.c_double), ('max_thrust', C.c_double),

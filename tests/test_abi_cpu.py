@@ -92,9 +92,22 @@ def test_state_layout(lib):
     assert lib.pdx_rollout_bytes(C.byref(c), 64) == (51 + 51) * 4 + 64 * ((34 + 2) * 4 + 16 + 2)
 
 
+def test_pid_control_modes_add_twelve_state_words(lib):
+    """AttitudeRate / Attitude (envs/control.py:120-287): integrals and last errors of both loops."""
+    fw, nw = C.c_int(), C.c_int()
+    base = pds.EnvConfig('DroneHoverBulletEnv-v0').to_pdx()
+    assert lib.pdx_state_field(C.byref(base), b'pid', C.byref(fw), C.byref(nw)) != 0
+    for mode, code in (('AttitudeRate', 1), ('Attitude', 2)):
+        c = pds.EnvConfig('DroneHoverBulletEnv-v0', control_mode=mode, aggregate_phy_steps=4).to_pdx()
+        assert c.control_mode == code and c.agg == 4
+        assert lib.pdx_state_field(C.byref(c), b'pid', C.byref(fw), C.byref(nw)) == 0 and nw.value == 12
+        assert lib.pdx_state_quads(C.byref(c)) >= lib.pdx_state_quads(C.byref(base)) + 3 - 1
+        assert c.obs_dim == base.obs_dim
+
+
 def test_unsupported_configurations_are_rejected(lib):
     with pytest.raises(NotImplementedError):
-        pds.EnvConfig('DroneHoverSimpleEnv-v0', control_mode='Attitude')
+        pds.EnvConfig('DroneHoverSimpleEnv-v0', control_mode='Position')
     with pytest.raises(KeyError):
         pds.EnvConfig('DroneFooEnv-v0')
     with pytest.raises(L.PhoenixB200Error):

@@ -115,7 +115,8 @@ def test_float64_matches_reference_goldens(name):
 
 
 F32_CASES = ['config1_hover_simple_default', 'config1_hover_simple_det', 'circle_simple_default',
-             'takeoff_simple_det', 'hover_bullet_default', 'hover_simple_nearhover_det']
+             'takeoff_simple_det', 'hover_bullet_default', 'hover_simple_nearhover_det',
+             'hover_simple_attrate', 'circle_bullet_attrate_agg4']
 
 
 @pytest.mark.parametrize('name', F32_CASES)
