@@ -339,8 +339,23 @@ def run_gpu_arm(a):
     bytes_per_launch = env.rollout_bytes(steps_per_launch) * n
     us_per_launch = ms * 1e3 / launches
     achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
+    traffic = None
+    try:                      # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this launch shape
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            tj = json.load(f)
+        if tj['env_steps_per_launch'] == steps_per_launch * n:
+            traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
+    except Exception:
+        pass
+    # issue-slot view of the same kernel (it is issue-bound, not HBM-bound): warp instructions per
+    # warp-step from the same ncu capture, against schedulers x clock
+    props = torch.cuda.get_device_properties(dev)
+    issue_peak = props.multi_processor_count * 4 * (clocks['sm_mhz'] or 1965) * 1e6
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
+                'traffic': traffic, 'algorithmic_bytes_per_launch': bytes_per_launch,
+                'issue': {'warp_inst_per_warp_step': 2229, 'source': 'profiles/r1_rollout_final_64k.summary.csv',
+                          'achieved_warp_inst_per_s': value / ctx.world / 32 * 2229, 'peak_warp_inst_per_s': issue_peak,
+                          'frac': value / ctx.world / 32 * 2229 / issue_peak}, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
                 'env_steps_per_launch': steps_per_launch * n, 'bytes_per_env_step': bytes_per_launch / (steps_per_launch * n),
                 'us_per_launch': us_per_launch, 'peak_source': peak_src}
 
