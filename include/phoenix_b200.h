@@ -203,6 +203,27 @@ int pdx_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint
 int pdx_moments(int64_t rows, int32_t dim, const float* x, const double* shift,
                 double* out, void* stream);
 
+/* ActorCritic.step (algs/core.py:370-393) fused into one launch: standardise the observation
+ * ((o - mean) / (std + eps), utils/online_mean_std.py:42-48; std == NULL skips it), Gaussian actor
+ * MLP (two hidden layers, relu), critic MLP (two hidden layers, tanh), a = mu + exp(log_std) * N(0,1)
+ * drawn with Philox keyed by (seed, env index, counter), log-probability.  Weights are torch
+ * nn.Linear tensors ([out][in] row-major float32) on the device; hidden sizes <= 64, n_out <= 4.
+ * obs [n][obs_dim] float32; actions [n][4], values [n], logp [n], mu_out [n][4] (optional). */
+typedef struct PdxMlp {
+  int32_t hidden[2];
+  int32_t n_out;
+  int32_t reserved;
+  const float* weight[3];
+  const float* bias[3];
+} PdxMlp;
+/* `packed`: device buffer of pdx_policy_pack_words() floats holding the weights transposed and zero
+ * padded as the kernel stages them; refresh it with pdx_policy_pack after every weight update. */
+int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v);
+int pdx_policy_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, float* packed, void* stream);
+int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                    const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
+                    uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
+
 /* Cross-rank combination of the 8-word episode statistics (utils/mpi_tools.py:217-240 does four
  * MPI all-reduces per key): the caller all-gathers the per-rank vectors into gathered[world][8]
  * (one NCCL call) and this writes out[0..4) = sums, out[4], out[6] = minima, out[5], out[7] = maxima. */

@@ -131,3 +131,239 @@ extern "C" int pdx_stats_combine(int32_t world, const double* gathered, double* 
   k_stats_combine<<<1, 32, 0, (cudaStream_t)stream>>>(world, gathered, out);
   return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
 }
+
+// =============================================================================================
+//  Fused policy step: ActorCritic.step (algs/core.py:370-393) for N environments in one launch:
+//  observation standardisation (utils/online_mean_std.py:42-48), Gaussian actor MLP (two hidden
+//  layers, relu; core.py:227-289), critic MLP (two hidden layers, tanh; core.py:297-310), action
+//  sample a = mu + exp(log_std) * eps with on-device Philox draws, and log-probability.
+//  One thread per environment.  Weights live in shared memory transposed to [in][out] so that a
+//  warp reads them as 128-bit broadcasts; a layer streams its inputs one at a time (from global
+//  memory for the first layer, from a per-thread shared column for the hidden ones) and keeps its
+//  <= 64 output accumulators in registers.
+// =============================================================================================
+namespace {
+
+constexpr int kPolBlock = 256;
+constexpr int kHidMax = 64;
+
+__device__ __forceinline__ uint4 pol_philox(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1): two MUFU operations, ~1e-6 absolute error (tanhf costs ~30
+// instructions and there are 128 activations per environment).
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+// acc[j] += sum_i Wt[i][j] * x_i ; inputs x_i come from `in(i)`.
+template <int OUT, class F>
+__device__ __forceinline__ void dense(const float* __restrict__ wt, const float* __restrict__ bias, int n_in, F in,
+                                      float (&acc)[OUT]) {
+#pragma unroll
+  for (int j = 0; j < OUT; ++j) acc[j] = bias[j];
+  for (int i = 0; i < n_in; ++i) {
+    const float x = in(i);
+    const float4* row = reinterpret_cast<const float4*>(wt + i * OUT);
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; ++j4) {
+      const float4 wv = row[j4];
+      acc[4 * j4 + 0] = fmaf(wv.x, x, acc[4 * j4 + 0]);
+      acc[4 * j4 + 1] = fmaf(wv.y, x, acc[4 * j4 + 1]);
+      acc[4 * j4 + 2] = fmaf(wv.z, x, acc[4 * j4 + 2]);
+      acc[4 * j4 + 3] = fmaf(wv.w, x, acc[4 * j4 + 3]);
+    }
+  }
+}
+
+struct PolArgs {
+  int64_t n;
+  int32_t obs_dim, act_dim, pi_h1, pi_h2, v_h1, v_h2;
+  const float* obs;
+  const float* mean;
+  const float* std;         // nullptr: no standardisation
+  float eps;
+  const float* pi_w[3]; const float* pi_b[3];
+  const float* v_w[3]; const float* v_b[3];
+  const float* log_std;
+  const float* packed;      // [pi_words + v_words] packed weights (k_pack_policy)
+  uint64_t seed, counter;
+  float* act; float* val; float* logp; float* mu;
+};
+
+// shared layout (floats): norm_mean[D], norm_inv[D], then per net: W1t[D][H], b1[H], W2t[H][H], b2[H], W3t[H][O4], b3[O4],
+// then hid[kHidMax][kPolBlock]
+template <int H>
+__device__ __forceinline__ void run_net(const float* __restrict__ sm_net, const float* __restrict__ obs_row,
+                                        const float* __restrict__ nmean, const float* __restrict__ ninv, int D, int h1, int h2,
+                                        bool tanh_act, float* __restrict__ hid, int tid, float (&out)[4]) {
+  const float* w1 = sm_net;
+  const float* b1 = w1 + D * H;
+  const float* w2 = b1 + H;
+  const float* b2 = w2 + H * H;
+  const float* w3 = b2 + H;
+  const float* b3 = w3 + H * 4;
+  float acc[H];
+  dense<H>(w1, b1, D, [&](int i) { return (__ldg(obs_row + i) - nmean[i]) * ninv[i]; }, acc);
+#pragma unroll
+  for (int j = 0; j < H; ++j) hid[j * kPolBlock + tid] = tanh_act ? fast_tanh(acc[j]) : fmaxf(acc[j], 0.0f);
+  dense<H>(w2, b2, h1, [&](int i) { return hid[i * kPolBlock + tid]; }, acc);
+  // every thread owns its hid column: no barrier needed between the read loop above and these writes
+#pragma unroll
+  for (int j = 0; j < H; ++j) hid[j * kPolBlock + tid] = tanh_act ? fast_tanh(acc[j]) : fmaxf(acc[j], 0.0f);
+  dense<4>(w3, b3, h2, [&](int i) { return hid[i * kPolBlock + tid]; }, out);
+}
+
+// Packs torch nn.Linear weights ([out][in]) into the kernel's shared-memory image: per net
+// W1t[D][H], b1[H], W2t[H][H], b2[H], W3t[H][4], b3[4], zero padded to H (52 or 64).
+template <int HP, int HV>
+__global__ void k_pack_policy(const PolArgs a, float* __restrict__ out) {
+  const int D = a.obs_dim;
+  const int pi_words = D * HP + HP + HP * HP + HP + HP * 4 + 4;
+  auto pack = [&](float* net, int H, const float* const* w, const float* const* b, int h1, int h2, int n_out) {
+    float* w1 = net; float* b1 = w1 + D * H; float* w2 = b1 + H; float* b2 = w2 + H * H; float* w3 = b2 + H; float* b3 = w3 + H * 4;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int k = tid; k < D * H; k += nt) { const int i = k / H, j = k % H; w1[k] = j < h1 ? w[0][j * D + i] : 0.0f; }
+    for (int k = tid; k < H; k += nt) { b1[k] = k < h1 ? b[0][k] : 0.0f; b2[k] = k < h2 ? b[1][k] : 0.0f; }
+    for (int k = tid; k < H * H; k += nt) { const int i = k / H, j = k % H; w2[k] = (j < h2 && i < h1) ? w[1][j * h1 + i] : 0.0f; }
+    for (int k = tid; k < H * 4; k += nt) { const int i = k / 4, j = k % 4; w3[k] = (j < n_out && i < h2) ? w[2][j * h2 + i] : 0.0f; }
+    if (tid < 4) b3[tid] = tid < n_out ? b[2][tid] : 0.0f;
+  };
+  pack(out, HP, a.pi_w, a.pi_b, a.pi_h1, a.pi_h2, a.act_dim);
+  pack(out + pi_words, HV, a.v_w, a.v_b, a.v_h1, a.v_h2, 1);
+}
+
+template <int HP, int HV>
+__global__ void __launch_bounds__(kPolBlock) k_policy(const PolArgs a) {
+  extern __shared__ __align__(16) float pol_sm[];
+  const int D = a.obs_dim, tid = threadIdx.x;
+  float* nmean = pol_sm;
+  float* ninv = nmean + ((D + 3) & ~3);
+  float* pi_net = ninv + ((D + 3) & ~3);
+  const int pi_words = D * HP + HP + HP * HP + HP + HP * 4 + 4;
+  float* v_net = pi_net + pi_words;
+  const int v_words = D * HV + HV + HV * HV + HV + HV * 4 + 4;
+  float* hid = v_net + v_words;
+  // ---- stage the normaliser and the packed (zero padded, transposed) weights: a flat copy of the
+  // blob k_pack_policy prepared (layout == the shared-memory plan from pi_net on)
+  for (int i = tid; i < D; i += kPolBlock) {
+    nmean[i] = a.std ? a.mean[i] : 0.0f;
+    ninv[i] = a.std ? 1.0f / (a.std[i] + a.eps) : 1.0f;
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.packed);
+    float4* dst = reinterpret_cast<float4*>(pi_net);
+    for (int k = tid; k < (pi_words + v_words) / 4; k += kPolBlock) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kPolBlock + tid;
+  if (i >= a.n) return;
+  const float* row = a.obs + i * D;
+  float mu[4], vv[4];
+  run_net<HP>(pi_net, row, nmean, ninv, D, a.pi_h1, a.pi_h2, false, hid, tid, mu);
+  run_net<HV>(v_net, row, nmean, ninv, D, a.v_h1, a.v_h2, true, hid, tid, vv);
+  // ---- sample: a = mu + std * eps, log p = sum(-eps^2/2 - log_std - log(2 pi)/2)
+  const uint4 r = pol_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+                             make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+  float eps[4];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float u1 = ((float)(rw[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(rw[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    eps[2 * p] = rad * c; eps[2 * p + 1] = rad * s;
+  }
+  float lp = 0.0f;
+  float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* av = reinterpret_cast<float*>(&act);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < a.act_dim) {
+      const float ls = a.log_std[k];
+      av[k] = mu[k] + expf(ls) * eps[k];
+      lp += -0.5f * eps[k] * eps[k] - ls - 0.9189385332046727f;
+    }
+  }
+  reinterpret_cast<float4*>(a.act)[i] = act;
+  a.val[i] = vv[0];
+  a.logp[i] = lp;
+  if (a.mu) reinterpret_cast<float4*>(a.mu)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+}
+
+template <int HP, int HV>
+int launch_policy(const PolArgs& a, cudaStream_t st) {
+  const int D = a.obs_dim;
+  const size_t words = 2 * ((D + 3) & ~3) + (size_t)(D * HP + HP + HP * HP + HP + HP * 4 + 4) +
+                       (size_t)(D * HV + HV + HV * HV + HV + HV * 4 + 4) + (size_t)kHidMax * kPolBlock;
+  const size_t smem = words * sizeof(float);
+  if (smem > (size_t)227 * 1024) return PDX_ERR_INVALID;
+  static size_t set = 0;
+  if (smem > set) {
+    if (cudaFuncSetAttribute(k_policy<HP, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PDX_ERR_CUDA;
+    set = smem;
+  }
+  if (a.n == 0) {                                     // pack only
+    k_pack_policy<HP, HV><<<8, 256, 0, st>>>(a, const_cast<float*>(a.packed));
+    return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  }
+  const unsigned grid = (unsigned)((a.n + kPolBlock - 1) / kPolBlock);
+  k_policy<HP, HV><<<grid, kPolBlock, smem, st>>>(a);
+  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+}
+
+}  // namespace
+
+static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                           const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
+                           uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
+
+extern "C" int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v) {
+  if (obs_dim <= 0 || !pi || !v) return PDX_ERR_INVALID;
+  const int64_t D = obs_dim, HP = (pi->hidden[0] <= 52 && pi->hidden[1] <= 52) ? 52 : 64, HV = 64;
+  return (D * HP + HP + HP * HP + HP + HP * 4 + 4) + (D * HV + HV + HV * HV + HV + HV * 4 + 4);
+}
+
+extern "C" int pdx_policy_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, float* packed, void* stream) {
+  if (!packed) return PDX_ERR_INVALID;
+  return policy_dispatch(0, obs_dim, packed, nullptr, nullptr, 0.f, pi, v, packed, packed, 0, 0, packed, packed, packed, nullptr, stream);
+}
+
+extern "C" int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                               const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
+                               uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
+  if (n <= 0) return PDX_ERR_INVALID;
+  return policy_dispatch(n, obs_dim, obs, mean, std, eps, pi, v, log_std, packed, seed, counter, actions, values, logp, mu_out, stream);
+}
+
+static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                           const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
+                           uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
+  if (n < 0 || obs_dim <= 0 || !obs || !pi || !v || !log_std || !packed || !actions || !values || !logp) return PDX_ERR_INVALID;
+  if (pi->hidden[0] < 1 || pi->hidden[0] > kHidMax || pi->hidden[1] < 1 || pi->hidden[1] > kHidMax || pi->n_out < 1 || pi->n_out > 4)
+    return PDX_ERR_INVALID;
+  if (v->hidden[0] < 1 || v->hidden[0] > kHidMax || v->hidden[1] < 1 || v->hidden[1] > kHidMax || v->n_out != 1) return PDX_ERR_INVALID;
+  const int rc = select_device_of(obs);
+  if (rc) return rc;
+  PolArgs a;
+  a.n = n; a.obs_dim = obs_dim; a.act_dim = pi->n_out;
+  a.pi_h1 = pi->hidden[0]; a.pi_h2 = pi->hidden[1]; a.v_h1 = v->hidden[0]; a.v_h2 = v->hidden[1];
+  a.obs = obs; a.mean = mean; a.std = std; a.eps = eps;
+  for (int k = 0; k < 3; ++k) { a.pi_w[k] = pi->weight[k]; a.pi_b[k] = pi->bias[k]; a.v_w[k] = v->weight[k]; a.v_b[k] = v->bias[k]; }
+  a.log_std = log_std; a.packed = packed; a.seed = seed; a.counter = counter;
+  a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
+  const bool pi_small = a.pi_h1 <= 52 && a.pi_h2 <= 52;
+  return pi_small ? launch_policy<52, 64>(a, (cudaStream_t)stream) : launch_policy<64, 64>(a, (cudaStream_t)stream);
+}

@@ -62,6 +62,11 @@ class PdxBuffers(C.Structure):
     ]
 
 
+class PdxMlp(C.Structure):
+    _fields_ = [('hidden', C.c_int32 * 2), ('n_out', C.c_int32), ('reserved', C.c_int32),
+                ('weight', C.c_void_p * 3), ('bias', C.c_void_p * 3)]
+
+
 _lib = None
 
 
@@ -99,6 +104,12 @@ def load():
                             C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_moments.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pdx_policy_step.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, P(PdxMlp), P(PdxMlp),
+                                    C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    lib.pdx_policy_pack_words.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp)]
+    lib.pdx_policy_pack_words.restype = C.c_int64
+    lib.pdx_policy_pack.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp), C.c_void_p, C.c_void_p]
     lib.pdx_stats_combine.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.pdx_abi_version() != ABI_VERSION:
         raise PhoenixB200Error(f'ABI mismatch: library {lib.pdx_abi_version()} != binding {ABI_VERSION}')
@@ -118,5 +129,5 @@ EXPORTED_SYMBOLS = [
     'pdx_config_finalize', 'pdx_state_quads', 'pdx_state_field', 'pdx_tape_slots',
     'pdx_step_bytes', 'pdx_rollout_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step',
     'pdx_step_many', 'pdx_dump_draws',
-    'pdx_gae', 'pdx_moments', 'pdx_stats_combine',
+    'pdx_gae', 'pdx_moments', 'pdx_stats_combine', 'pdx_policy_step', 'pdx_policy_pack', 'pdx_policy_pack_words',
 ]

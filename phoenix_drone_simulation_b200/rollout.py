@@ -175,8 +175,13 @@ def _mlp(sizes, act):
 
 class ActorCritic(torch.nn.Module):
     def __init__(self, obs_dim, act_dim=4, pi_hidden=(50, 50), v_hidden=(64, 64), device='cuda',
-                 use_standardized_obs=True, use_scaled_rewards=True, dist=None):
+                 use_standardized_obs=True, use_scaled_rewards=True, dist=None, fused=True, seed=0):
         super().__init__()
+        # fused: one CUDA kernel (pdx_policy_step) does standardise + both MLPs + sample + log-prob;
+        # the torch modules below stay the owners of the weights (training updates them in place)
+        self.fused = (fused and len(pi_hidden) == 2 and len(v_hidden) == 2 and max(*pi_hidden, *v_hidden) <= 64
+                      and act_dim <= 4)
+        self.seed, self._counter = int(seed), 0
         self.pi = _mlp([obs_dim, *pi_hidden, act_dim], torch.nn.ReLU)
         self.v = _mlp([obs_dim, *v_hidden, 1], torch.nn.Tanh)
         self.log_std = torch.nn.Parameter(torch.full((act_dim,), math.log(0.5)), requires_grad=False)
@@ -194,9 +199,86 @@ class ActorCritic(torch.nn.Module):
             o = self.obs_oms(o)
         return self.v(o).squeeze(-1)
 
+    def _mlp_struct(self, net, n_out):
+        lins = [m for m in net if isinstance(m, torch.nn.Linear)]
+        st = _lib.PdxMlp()
+        st.hidden[0], st.hidden[1], st.n_out = lins[0].out_features, lins[1].out_features, n_out
+        for k, lin in enumerate(lins):
+            assert lin.weight.is_contiguous() and lin.weight.dtype == torch.float32
+            st.weight[k], st.bias[k] = lin.weight.data_ptr(), lin.bias.data_ptr()
+        return st
+
+    def _packed_weights(self, obs_dim, pi, v, stream):
+        """Device blob of the transposed / padded weights, re-packed when a parameter changed
+        (torch bumps `_version` on every in-place update)."""
+        params = [p_ for net in (self.pi, self.v) for p_ in net.parameters()]
+        ver = tuple(p_._version for p_ in params) + tuple(p_.data_ptr() for p_ in params)
+        if getattr(self, '_pack_ver', None) != ver:
+            words = int(_lib.load().pdx_policy_pack_words(obs_dim, C.byref(pi), C.byref(v)))
+            if getattr(self, '_pack', None) is None or self._pack.numel() != words:
+                self._pack = torch.empty(words, dtype=torch.float32, device=params[0].device)
+            _lib.check(_lib.load().pdx_policy_pack(obs_dim, C.byref(pi), C.byref(v), C.c_void_p(self._pack.data_ptr()), stream))
+            self._pack_ver = ver
+        return self._pack
+
+    @torch.no_grad()
+    def step_into(self, obs, act, val, logp, mu=None):
+        """Fused ActorCritic.step: obs [N, D] float32 CUDA -> writes act [N, 4], val [N], logp [N]
+        (and optionally the Gaussian mean) in ONE kernel launch."""
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()
+        n, d = obs.shape
+        for t in (act, val, logp):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert act.shape == (n, 4)
+        pi, v = self._mlp_struct(self.pi, self.log_std.shape[0]), self._mlp_struct(self.v, 1)
+        self._counter += 1
+        oms = self.obs_oms
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        st = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        pack = self._packed_weights(d, pi, v, st)
+        _lib.check(_lib.load().pdx_policy_step(n, d, p(obs), p(oms.mean) if oms else None, p(oms.std) if oms else None,
+                                               oms.eps if oms else 0.0, C.byref(pi), C.byref(v), p(self.log_std.data),
+                                               p(pack), self.seed, self._counter, p(act), p(val), p(logp), p(mu), st))
+
+    def prepare_step_into(self, obs, act, val, logp):
+        """Handle for `step_prepared`: all ctypes arguments of one fused policy step, built once.
+        Valid while the tensors and the (in place updated) parameters stay where they are."""
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and act.shape == (obs.shape[0], 4)
+        pi, v = self._mlp_struct(self.pi, self.log_std.shape[0]), self._mlp_struct(self.v, 1)
+        oms = self.obs_oms
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        st = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        pack = self._packed_weights(obs.shape[1], pi, v, st)
+        head = (obs.shape[0], obs.shape[1], p(obs), p(oms.mean) if oms else None, p(oms.std) if oms else None,
+                oms.eps if oms else 0.0, C.byref(pi), C.byref(v), p(self.log_std.data), p(pack), self.seed)
+        tail = (p(act), p(val), p(logp), None)
+        return (head, tail, pi, v, obs, act, val, logp)
+
+    def refresh_packed_weights(self, obs_dim, stream=None):
+        """Call after an optimiser step when prepared handles are in use (the blob keeps its address)."""
+        pi, v = self._mlp_struct(self.pi, self.log_std.shape[0]), self._mlp_struct(self.v, 1)
+        self._packed_weights(obs_dim, pi, v, stream or C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def step_prepared(self, handle, stream):
+        self._counter += 1
+        rc = self._lib_policy(*handle[0], self._counter, *handle[1], stream)
+        if rc:
+            _lib.check(rc)
+
+    @property
+    def _lib_policy(self):
+        return _lib.load().pdx_policy_step
+
     @torch.no_grad()
     def step(self, obs, generator=None):
         """obs [N, D] on device -> (action [N, 4], value [N], logp [N]), all on device."""
+        if self.fused and obs.is_cuda and generator is None and obs.dtype == torch.float32 and self.log_std.shape[0] == 4:
+            n = obs.shape[0]
+            act = torch.empty((n, 4), dtype=torch.float32, device=obs.device)
+            val = torch.empty(n, dtype=torch.float32, device=obs.device)
+            logp = torch.empty(n, dtype=torch.float32, device=obs.device)
+            self.step_into(obs.contiguous(), act, val, logp)
+            return act, val, logp
         o = obs.float()
         if self.obs_oms:
             o = self.obs_oms(o)
@@ -238,8 +320,16 @@ class RolloutCollector:
         self._started = False
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs = None
+        self._prepared = None
+
+    def _fused(self, generator=None):
+        return (self.ac.fused and generator is None and self.env.dtype == torch.float32
+                and self.ac.log_std.shape[0] == 4)
 
     def _policy_step(self, t, generator=None):
+        if self._fused(generator):
+            self.ac.step_into(self.obs[t], self.act[t], self.val[t], self.logp[t])
+            return
         a, v, logp = self.ac.step(self.obs[t], generator)
         self.act[t], self.val[t], self.logp[t] = a, v, logp
 
@@ -271,10 +361,23 @@ class RolloutCollector:
         env.clear_episode_stats()
         self.boot.zero_()
         limit = env.max_episode_steps
-        graphs = self.use_cuda_graphs and generator is None
+        fused = self._fused(generator)
+        graphs = self.use_cuda_graphs and generator is None and not fused
         if graphs and self._graphs is None:
             self._capture()
+        if fused and self._prepared is None:
+            self._prepared = [(ac.prepare_step_into(self.obs[t], self.act[t], self.val[t], self.logp[t]),
+                               env.prepare_step(self.act[t], self._outs[t])) for t in range(T)]
+        stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        if fused:
+            ac.refresh_packed_weights(env.obs_dim, stream)
         for t in range(T):
+            if fused:                                    # two prepared C-ABI launches per step
+                ac.step_prepared(self._prepared[t][0], stream)
+                env.step_prepared(self._prepared[t][1], stream)
+                if (not self.reset_each_rollout) or t + 1 >= limit or env.cfg.reset_on_nonfinite:
+                    self.boot[t] = ac.value(env.final_obs) * self.trunc[t].float()
+                continue
             if graphs:
                 self._graphs[t].replay()
             else:

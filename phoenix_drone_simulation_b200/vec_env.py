@@ -163,6 +163,24 @@ class VecEnv:
             info['final_observation'] = self.final_obs
         return self.obs, self.reward, self.terminated, self.truncated, info
 
+    # ---- prepared launches: everything that does not change between calls is built once ------
+    def prepare_step(self, actions, out):
+        """Returns a handle for `step_prepared`: the PdxBuffers of a step that reads `actions`
+        [N, 4] and writes into the tensors of `out` (see `step`).  The tensors must stay alive."""
+        assert actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, 4)
+        buf = _lib.PdxBuffers.from_buffer_copy(self._buf)
+        for k, t in out.items():
+            assert t.is_cuda and t.is_contiguous() and t.shape[0] == self.num_envs, k
+            setattr(buf, k, t.data_ptr())
+        return (C.byref(self.pdx), C.byref(buf), C.c_void_p(actions.data_ptr()), buf, actions, out)
+
+    def step_prepared(self, handle, stream):
+        """`stream`: C.c_void_p of the CUDA stream (cache it: looking it up costs microseconds)."""
+        self._counter += 1
+        rc = self.lib.pdx_step(handle[0], handle[1], handle[2], self.seed, self._counter, stream)
+        if rc:
+            _lib.check(rc)
+
     def step_many(self, actions, out):
         """T env.steps of every environment in ONE kernel launch (state stays in registers
         between steps; open-loop action sequence).  actions: float32 CUDA tensor [T, N, 4];

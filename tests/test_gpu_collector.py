@@ -83,6 +83,34 @@ def test_online_mean_std_on_device_matches_reference(name):
     np.testing.assert_allclose(oms(_cuda(g['probe'])).cpu().numpy(), g['forward'], rtol=1e-4, atol=1e-5)
 
 
+def test_fused_policy_step_matches_torch_modules():
+    """pdx_policy_step (standardise + actor MLP + critic MLP + sample + log-prob in one kernel)
+    against the torch modules that own the weights; float32, tolerance 2e-5 abs on mean / value."""
+    from phoenix_drone_simulation_b200.rollout import ActorCritic
+    torch.manual_seed(1)
+    for obs_dim, pi_h, v_h, n in ((34, (50, 50), (64, 64), 5000), (160, (64, 64), (64, 32), 777), (17, (8, 50), (3, 64), 256)):
+        ac = ActorCritic(obs_dim, pi_hidden=pi_h, v_hidden=v_h, device='cuda', seed=3)
+        ac.obs_oms.mean.copy_(torch.randn(obs_dim, device='cuda') * 0.3)
+        ac.obs_oms.std.copy_(torch.rand(obs_dim, device='cuda') + 0.5)
+        ac.set_log_std(0.7)
+        obs = torch.randn((n, obs_dim), device='cuda') * 2
+        act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
+        mu = torch.empty((n, 4), device='cuda')
+        ac.step_into(obs, act, val, logp, mu)
+        o = ac.obs_oms(obs)
+        torch.testing.assert_close(mu, ac.pi(o), rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(val, ac.v(o).squeeze(-1), rtol=1e-4, atol=2e-5)
+        std = torch.exp(ac.log_std)
+        ref_logp = torch.distributions.Normal(mu, std).log_prob(act).sum(-1)
+        torch.testing.assert_close(logp, ref_logp, rtol=1e-4, atol=1e-4)
+        z = ((act - mu) / std).flatten()
+        if n >= 5000:
+            assert abs(float(z.mean())) < 0.03 and abs(float(z.std()) - 1) < 0.03
+        act2 = torch.empty_like(act)
+        ac.step_into(obs, act2, val, logp)                      # next counter -> new draws
+        assert not torch.equal(act, act2)
+
+
 def test_collector_end_to_end_config5():
     """BASELINE config 5: DroneHoverBulletEnv-v0 driving a PPO rollout (reference networks), all on
     device.  Checks the stored fields against an independent recomputation."""
