@@ -142,3 +142,13 @@ def test_product_package_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_empty_batch_is_rejected_before_any_cuda_call(lib):
+    """n_envs = 0 (the 'empty input' edge case) is an argument error, reported without a device."""
+    c = pds.EnvConfig('DroneHoverSimpleEnv-v0').to_pdx()
+    b = L.PdxBuffers()
+    b.n_envs = 0
+    assert lib.pdx_step(C.byref(c), C.byref(b), None, 0, 0, None) == -1
+    assert b'n_envs' in lib.pdx_last_error()
+    assert lib.pdx_step_many(C.byref(c), C.byref(b), None, 0, 0, 0, None) == -1

@@ -367,3 +367,36 @@ def test_step_many_equals_repeated_step(env_id, kw):
         assert torch.equal(a.state, b.state)
         assert torch.equal(a.episode_stats()[:4], b.episode_stats()[:4]) or torch.allclose(a.episode_stats(), b.episode_stats())
         assert int(a.episode_stats()[0]) == n_fin and n_fin > 0
+
+
+@pytest.mark.parametrize('env_id', ['DroneHoverSimpleEnv-v0', 'DroneHoverBulletEnv-v0', 'DroneCircleSimpleEnv-v0',
+                                    'DroneCircleBulletEnv-v0', 'DroneTakeOffSimpleEnv-v0', 'DroneTakeOffBulletEnv-v0'])
+def test_edge_shapes_all_ids(env_id):
+    """Ragged / minimal / maximal shapes for every env id: 1 env, 33 envs (two warps, one ragged),
+    history 1 and the maximum 16, both dtypes, PWM and PID control; single-step launches and one
+    fused launch must agree bit for bit and stay finite; odd N*D falls back from the bulk copy."""
+    for n, H, dtype, mode in ((1, 2, torch.float64, 'PWM'), (33, 1, torch.float32, 'PWM'),
+                              (33, 16, torch.float32, 'AttitudeRate'), (5, 3, torch.float64, 'Attitude')):
+        kw = dict(observation_history_size=H, control_mode=mode, max_episode_steps=11)
+        a = _vec(env_id, n, seed=21, dtype=dtype, **kw)
+        b = _vec(env_id, n, seed=21, dtype=dtype, **kw)
+        assert a.obs_dim == H * (a.core_dim + 4)
+        assert torch.equal(a.reset(), b.reset())
+        T = 14
+        g = torch.Generator(device='cuda').manual_seed(n)
+        acts = (a.cfg.hover_action + 0.2 * torch.randn((T, n, 4), device='cuda', generator=g)).contiguous()
+        out = {'obs': torch.zeros((T, n, a.obs_dim), dtype=dtype, device='cuda'),
+               'reward': torch.zeros((T, n), dtype=dtype, device='cuda'), 'cost': torch.zeros((T, n), dtype=dtype, device='cuda'),
+               'terminated': torch.zeros((T, n), dtype=torch.uint8, device='cuda'),
+               'truncated': torch.zeros((T, n), dtype=torch.uint8, device='cuda')}
+        b.step_many(acts, out)
+        n_trunc = 0
+        for t in range(T):
+            o, r, te, tr, _ = a.step(acts[t])
+            assert torch.isfinite(o).all() and torch.isfinite(r).all()
+            assert torch.equal(o, out['obs'][t]) and torch.equal(r, out['reward'][t]), (env_id, n, H, t)
+            assert torch.equal(tr, out['truncated'][t].bool())
+            n_trunc += int(tr.sum())
+        if 'TakeOff' in env_id:
+            assert n_trunc == n                     # never terminates: the time limit fires once in 14 steps
+        assert torch.equal(a.state, b.state)
