@@ -86,6 +86,21 @@ def ppo_rollout(n, T, rollouts, warmup):
             'episodes_in_last_rollout': es.n, 'ep_ret_mean': es.ret_mean, 'ep_len_mean': es.len_mean}
 
 
+def ppo_training(n, T, epochs):
+    """PPO end-to-end FPS (env-steps/s INCLUDING the SGD update) on
+    DroneCircleBulletEnv-v0 with PWM control; the reference's logs: median 30,916 (unknown CPU host)."""
+    from phoenix_drone_simulation_b200.ppo import PPO
+    alg = PPO('DroneCircleBulletEnv-v0', num_envs=n, steps=T, epochs=epochs, seed=0)
+    alg.learn()
+    fps = sorted(r['FPS'] for r in alg.history[1:])
+    return {'env_id': 'DroneCircleBulletEnv-v0', 'envs': n, 'rollout_steps': T, 'epochs': epochs,
+            'what': 'PPO training: rollout (fused policy + env kernels, GAE) + torch update (80 full-batch policy '
+                    'steps, 5 x 16 value mini-batch steps, iwpg.py defaults); env-steps/s including the update',
+            'env_steps_per_s': fps[len(fps) // 2], 'published_reference_fps': 30916,
+            'first_epoch': {k: alg.history[0][k] for k in ('EpRet', 'EpLen', 'episodes')},
+            'last_epoch': {k: alg.history[-1][k] for k in ('EpRet', 'EpLen', 'episodes')}}
+
+
 def main():
     p = argparse.ArgumentParser()
     p.add_argument('--scale', type=float, default=1.0, help='scale the env counts (smoke runs)')
@@ -102,6 +117,7 @@ def main():
     emit(dict(config='configs[1] fixed policy', **open_loop('DroneHoverSimpleEnv-v0', sc(65536), 64, a.steps * 4, a.warmup,
                                                            lambda s, d, g: -0.1111 + 0.05 * torch.randn(s, device=d, generator=g))))
     emit(dict(config='configs[4]', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1)))
+    emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))
 
 
 if __name__ == '__main__':
