@@ -108,7 +108,7 @@ class PPO:
                     kl = float(kl_t)
                 if kl > self.target_kl:
                     break
-        return {'loss_v': float(loss_v), 'loss_pi': float(loss_pi), 'pi_iters': it + 1, 'kl': kl}
+        return {'loss_v': float(loss_v.detach()), 'loss_pi': float(loss_pi.detach()), 'pi_iters': it + 1, 'kl': kl}
 
     def learn_one_epoch(self):
         t0 = time.perf_counter()
