@@ -69,7 +69,7 @@ static LaunchShape pick_shape(int D) {
   int forced = 0;
   if (const char* e = getenv("PDX_BLOCK")) {          // tuning hook: 32 / 64 / 128 / 256
     const int b = atoi(e);
-    if (b == 32 || b == 64 || b == 128 || b == 256) forced = b;
+    if (b >= 32 && b <= kMaxBlock && b % 32 == 0) forced = b;
   }
   LaunchShape best{0, 0, 0};
   int best_warps = -1;

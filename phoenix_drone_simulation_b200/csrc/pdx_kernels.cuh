@@ -17,7 +17,7 @@
 
 namespace pdx {
 
-constexpr int kMaxBlock = 256;     // threads per block are chosen at run time (<= kMaxBlock)
+constexpr int kMaxBlock = 512;     // threads per block are chosen at run time (<= kMaxBlock)
 
 template <class T>
 struct KArgs {
@@ -371,7 +371,7 @@ __host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_til
 //  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
-__global__ void __launch_bounds__(kMaxBlock, 2) k_rollout(const KArgs<T> a) {
+__global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
