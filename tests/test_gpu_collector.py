@@ -167,3 +167,22 @@ def test_ppo_learns_to_hover():
     assert all(math.isfinite(r['loss_v']) and math.isfinite(r['loss_pi']) for r in alg.history)
     assert last['episodes'] < 0.25 * first['episodes'], (first, last)
     assert last['EpLen'] > 2 * first['EpLen']
+
+
+def test_policy_json_on_device_and_batched_evaluator():
+    """The JSON golden (reference loader output) through the fused policy kernel, and the batched
+    EnvironmentEvaluator (utils/evaluation.py:52-107): deterministic, repeatable, sane ranges."""
+    from phoenix_drone_simulation_b200.policy_io import load_policy_json, evaluate
+    g = _load('policy_json')
+    ac = load_policy_json(os.path.join(GOLD, 'policy_json.json'), device='cuda')
+    n = g['obs'].shape[0]
+    act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
+    mu = torch.empty((n, 4), device='cuda')
+    ac.step_into(_cuda(g['obs']), act, val, logp, mu)
+    np.testing.assert_allclose(mu.cpu().numpy(), g['mu'], rtol=1e-4, atol=2e-5)
+    r1, l1, c1 = evaluate('DroneHoverSimpleEnv-v0', ac, num_evaluations=128, seed=3)
+    r2, l2, c2 = evaluate('DroneHoverSimpleEnv-v0', ac, num_evaluations=128, seed=3)
+    assert r1.shape == (128,) and np.isfinite(r1).all() and (l1 >= 1).all() and (l1 <= 500).all()
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(l1, l2)
+    assert (r1 < 0).all() and (c1 >= 0).all()
