@@ -263,7 +263,10 @@ class DistCtx:
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-            os.environ['NCCL_DEBUG'] = os.environ.get('PDX_NCCL_DEBUG', 'WARN')   # keep stdout to ONE JSON line
+            # keep stdout to ONE JSON line: NCCL prints its version banner there at any debug level
+            os.environ.pop('NCCL_DEBUG', None)
+            if os.environ.get('PDX_NCCL_DEBUG'):
+                os.environ['NCCL_DEBUG'] = os.environ['PDX_NCCL_DEBUG']
             dist.init_process_group('nccl', device_id=self.device)
             self.dist = dist
         else:
