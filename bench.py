@@ -252,6 +252,31 @@ def time_e2e(env, inner, K, W, dist_ctx, gen_seed):
     return ms, pipe['h2d_bytes'], pipe['d2h_bytes']
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Host side of the e2e leg: keep this rank's threads (and therefore its pinned staging buffers,
+    first-touch) on the NUMA node its GPU hangs off; otherwise eight ranks share one node's memory
+    controllers.  Best effort: silently skipped where sysfs does not tell."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f'{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class DistCtx:
     def __init__(self, n_gpus):
         import torch
@@ -259,6 +284,7 @@ class DistCtx:
         self.rank = int(os.environ.get('RANK', '0'))
         self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(self.local_rank)
+        self.numa_node = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
         self.device = torch.device('cuda', self.local_rank)
         if self.world > 1:
             import torch.distributed as dist
@@ -365,6 +391,7 @@ def run_gpu_arm(a):
     e2e_ms, h2d, d2h = time_e2e(env, a.inner, max(1, a.steps // a.e2e_div), a.warmup, ctx, 99 + ctx.rank)
     e2e_steps = max(1, a.steps // a.e2e_div) * a.inner * n * ctx.world
     e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'numa_node_rank0': ctx.numa_node,
            'api': 'VecEnv.step_many_host: pinned host action/obs/reward/cost/flag buffers, H2D + launch + D2H per 8-step chunk on three streams, all inside the timed region'}
 
     extra = {}
