@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
   T* acc_ext = tile0 + (size_t)NT * B * D + (size_t)(B >> 5) * (kResetRows * 4 * kResetChunk);
   const size_t off = (((size_t)NT * B * D + (size_t)(B >> 5) * kResetRows * 4 * kResetChunk + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
   double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
-  volatile int* s_tile_free = reinterpret_cast<volatile int*>(smem_raw + off + sizeof(double) * 4 * B);
+  int* s_tile_free = reinterpret_cast<int*>(smem_raw + off + sizeof(double) * 4 * B);   // accessed with atomics only
   unsigned char* s_fin_lane = smem_raw + off + sizeof(double) * 4 * B + 16 + (warp << 5);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
     // ---- the tile of this step was last read by the bulk copy of step t - n_tiles: thread 0
     // publishes the newest step whose copy has drained (it waits right after issuing each copy;
     // with a single tile the rows are shifted in place, ascending, once the previous copy left)
-    if (t >= NT) { while (*s_tile_free < t - NT) {} }
+    if (t >= NT) { while (atomicAdd(s_tile_free, 0) < t - NT) {} }
 
     // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319).
     // The tile has the row-major layout of the output, so lane l's row starts at bank l*D mod 32:
@@ -698,14 +698,14 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
       __syncthreads();
       if (tid == 0) {
         bulk_store(gdst, tile, bytes);
-        if (NT == 2) { bulk_wait_read<1>(); *s_tile_free = t - 1; }   // the copy issued one step ago has drained
-        else { bulk_wait_read<0>(); *s_tile_free = t; }
+        if (NT == 2) { bulk_wait_read<1>(); atomicExch(s_tile_free, t - 1); }   // the copy issued one step ago has drained
+        else { bulk_wait_read<0>(); atomicExch(s_tile_free, t); }
       }
     } else {
       __syncthreads();
       for (int e = tid; e < rows * D; e += B) gdst[e] = tile[e];
       __syncthreads();
-      if (tid == 0) *s_tile_free = t;
+      if (tid == 0) atomicExch(s_tile_free, t);
     }
   }
 
