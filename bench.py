@@ -66,15 +66,19 @@ def _cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
-def cpu_env_steps_per_sec(env_id, budget_s, procs=None, max_steps=0):
+def cpu_env_steps_per_sec(env_id, budget_s, procs=None, max_steps=0, pool=None):
     """Σ steps / wall over `procs` worker processes (default: all host cores)."""
     import multiprocessing as mp
     procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context('fork')
+    own = pool is None
+    if own:
+        pool = mp.get_context('fork').Pool(procs)
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(env_id, 1000 + 10000 * r, budget_s, max_steps) for r in range(procs)])
+    res = pool.map(_cpu_worker, [(env_id, 1000 + 10000 * r, budget_s, max_steps) for r in range(procs)], chunksize=1)
     wall = time.perf_counter() - t0
+    if own:
+        pool.close()
+        pool.join()
     steps = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
     return steps / busy, procs, steps, wall
@@ -84,16 +88,20 @@ def run_reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import multiprocessing as mp
     K, W = a.steps, a.warmup
     per_step_budget = min(2.0, 120.0 / max(1, K + W))          # whole run ends within minutes
     procs = os.cpu_count() or 1
+    pool = mp.get_context('fork').Pool(procs)
     for _ in range(W):
-        cpu_env_steps_per_sec(a.env_id, per_step_budget / 4, procs)
+        cpu_env_steps_per_sec(a.env_id, per_step_budget / 4, procs, pool=pool)
     tot_steps, tot_time = 0, 0.0
     for _ in range(K):
-        v, _, steps, _ = cpu_env_steps_per_sec(a.env_id, per_step_budget, procs)
+        v, _, steps, _ = cpu_env_steps_per_sec(a.env_id, per_step_budget, procs, pool=pool)
         tot_steps += steps
         tot_time += steps / v
+    pool.close()
+    pool.join()
     value = tot_steps / tot_time
     sample = (f'{K} samples of {per_step_budget:.2f} s on {procs} processes, one oracle env per process, '
               f'U(-1,1) float32 actions, auto-reset ({tot_steps} env-steps in total)')
