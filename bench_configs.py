@@ -116,6 +116,8 @@ def main():
                                               use_ground_effect=True, reset_on_nonfinite=True)))
     emit(dict(config='configs[1] fixed policy', **open_loop('DroneHoverSimpleEnv-v0', sc(65536), 64, a.steps * 4, a.warmup,
                                                            lambda s, d, g: -0.1111 + 0.05 * torch.randn(s, device=d, generator=g))))
+    emit(dict(config='configs[4] env only (open loop)', **open_loop('DroneHoverBulletEnv-v0', sc(131072), 32, a.steps, a.warmup,
+                                                               lambda s, d, g: 0.1111 + 0.3 * torch.randn(s, device=d, generator=g))))
     emit(dict(config='configs[4]', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1)))
     emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))
 
