@@ -7,11 +7,12 @@
 //     layout of the block's slice of the row-major [n_envs][obs_dim] output, and leave the SM
 //     as ONE bulk asynchronous copy (cp.async.bulk shared->global, the TMA engine; SASS UBLKCP)
 //     issued by one thread, double buffered so the copy of step t overlaps step t+1;
-//   * episodes that end are reset inside the same launch.  The reset path is long (two noisy
-//     observation calls, ~20 Philox calls), so finished environments of a block are compacted
-//     through shared memory and reset by the lanes of warp 0 instead of diverging every warp;
-//   * episode statistics are reduced by that warp with shuffles, one set of atomics per block
-//     and launch.
+//   * episodes that end are reset inside the same launch.  The reset path is as long as a step
+//     (two noisy observation calls, ~20 Philox calls) and only a few lanes of a warp need it, so
+//     the warp generates the random draws of its finished environments together (shared table,
+//     one Philox call per lane and pass) and only the arithmetic runs on the owner lanes;
+//   * episode statistics accumulate per thread in shared memory and are reduced once per launch
+//     (warp shuffles, one set of atomics per block).
 #pragma once
 #include "pdx_model.cuh"
 

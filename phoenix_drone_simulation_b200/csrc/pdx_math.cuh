@@ -262,15 +262,6 @@ __host__ __device__ constexpr bool reset_site_used(uint32_t site, int task, bool
   if (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 5) return noise;
   return false;
 }
-// compact list of the site rows a reset of this flavour draws (row = site - SITE_RESET)
-struct ResetSiteList { int n; unsigned char row[kResetRows]; };
-__host__ __device__ constexpr ResetSiteList make_reset_sites(int task, bool bullet, bool noise) {
-  ResetSiteList l{};
-  for (int r = 0; r < kResetRows; ++r)
-    if (reset_site_used(SITE_RESET + (uint32_t)r, task, bullet, noise)) l.row[l.n++] = (unsigned char)r;
-  return l;
-}
-
 template <class T>
 struct TableRng {
   static constexpr bool kTape = false;
