@@ -143,14 +143,19 @@ class ClockSampler:
                  'hw_power_brake': 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown'}
         return {k for k, attr in names.items() if mask & getattr(nv, attr, 0)}
 
-    def _loop(self):
+    def sample_once(self):
         nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.reasons |= self._reasons(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        except Exception:
+            pass
+
+    def _loop(self):
         while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.reasons |= self._reasons(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            except Exception:
-                pass
+            self.sample_once()
             time.sleep(0.002)
 
     def start(self):
@@ -216,8 +221,10 @@ def ring_slots(bytes_per_segment):
     return max(2, -(-2 * L2_BYTES // bytes_per_segment))
 
 
-def time_device(env, seg, K, W, dist_ctx):
-    """K segments timed with CUDA events on the launching stream; max over ranks."""
+def time_device(env, seg, K, W, dist_ctx, sampler=None):
+    """K segments timed with CUDA events on the launching stream; max over ranks.  `sampler`: clocks
+    are also read from this thread while the device works through the queued launches, so even a
+    very short timed region is sampled under load."""
     import torch
     launches = 0
     for k in range(W):
@@ -231,6 +238,10 @@ def time_device(env, seg, K, W, dist_ctx):
         launches += seg.run(W + k)
         dist_ctx.reduce_stats(env)
     e1.record()
+    if sampler is not None:
+        sampler.sample_once()
+        while not e1.query():
+            sampler.sample_once()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     dist_ctx.barrier()
@@ -368,7 +379,7 @@ def run_gpu_arm(a):
 
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
-    ms, launches = time_device(env, seg, a.steps, a.warmup, ctx)
+    ms, launches = time_device(env, seg, a.steps, a.warmup, ctx, sampler)
     clocks = sampler.stop()
     env_steps = a.steps * a.inner * n * ctx.world
     value = env_steps / (ms * 1e-3)
