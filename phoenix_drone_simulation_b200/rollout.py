@@ -353,6 +353,7 @@ class RolloutCollector:
 
     def collect(self, generator=None):
         env, ac, T = self.env, self.ac, self.T
+        torch.cuda.nvtx.range_push('pdx_collect')
         if self.reset_each_rollout or not self._started:
             self.obs[0].copy_(env.reset())
             self._started = True
@@ -394,6 +395,7 @@ class RolloutCollector:
         adv, target_v, disc_ret = compute_gae(self.rew, self.val, done, self.boot, last_val, self.gamma,
                                               self.lam, ret_std.item() if ret_std is not None else None)
         stats = allreduce_episode_stats(env.episode_stats(), self.dist)
+        torch.cuda.nvtx.range_pop()
         return {'obs': self.obs[:T], 'act': self.act, 'adv': adv, 'target_v': target_v, 'log_p': self.logp,
                 'discounted_ret': disc_ret, 'rew': self.rew, 'val': self.val, 'done': done,
                 'episode_stats': EpisodeStats(stats)}

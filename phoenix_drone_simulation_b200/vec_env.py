@@ -198,8 +198,10 @@ class VecEnv:
             assert t.is_cuda and t.is_contiguous() and t.shape[0] == T and t.shape[1] == self.num_envs, k
             setattr(buf, k, t.data_ptr())
         assert self.rng == 'philox', 'step_many draws on device'
+        torch.cuda.nvtx.range_push('pdx_step_many')         # shows up in nsys / ncu --nvtx timelines
         _lib.check(self.lib.pdx_step_many(C.byref(self.pdx), C.byref(buf), C.c_void_p(actions.data_ptr()), T,
                                           self.seed, self._counter + 1, self._stream()))
+        torch.cuda.nvtx.range_pop()
         self._counter += T
         return out
 

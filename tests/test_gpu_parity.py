@@ -405,3 +405,24 @@ def test_edge_shapes_all_ids(env_id):
         if 'TakeOff' in env_id:
             assert n_trunc == n                     # never terminates: the time limit fires once in 14 steps
         assert torch.equal(a.state, b.state)
+
+
+def test_checkpoint_resume_is_exact():
+    """state_dict / load_state_dict (checkpoint / resume): a restored engine continues the
+    interrupted run bit for bit -- state, RNG counter and episode statistics travel."""
+    N, T = 512, 9
+    env = _vec('DroneCircleBulletEnv-v0', N, seed=13)
+    env.reset()
+    g = torch.Generator(device='cuda').manual_seed(2)
+    acts = (torch.rand((2 * T, N, 4), device='cuda', generator=g) * 2 - 1).contiguous()
+    for t in range(T):
+        env.step(acts[t])
+    sd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in env.state_dict().items()}
+    ref = [tuple(x.clone() for x in env.step(acts[T + t])[:4]) for t in range(T)]
+    ref_stats = env.episode_stats().clone()
+    other = _vec('DroneCircleBulletEnv-v0', N, seed=999)        # different seed: everything must come from the dict
+    other.load_state_dict(sd)
+    for t in range(T):
+        o, r, te, tr, _ = other.step(acts[T + t])
+        assert torch.equal(o, ref[t][0]) and torch.equal(r, ref[t][1]) and torch.equal(te, ref[t][2]) and torch.equal(tr, ref[t][3])
+    assert torch.equal(other.episode_stats(), ref_stats)
