@@ -114,11 +114,13 @@ extern "C" int pdx_moments(int64_t rows, int32_t dim, const float* x, const doub
   if (rows <= 0 || dim <= 0 || dim > 1024 || !x || !out) return PDX_ERR_INVALID;
   const int rc = select_device_of(x);
   if (rc) return rc;
-  const int bx = ((dim + 31) / 32) * 32;
+  // blockDim = (dim, rows per block): thread (y, x) reads x[row * dim + x], so the linear thread id
+  // walks the row-major matrix contiguously -- every lane of every warp is busy whatever dim is
+  const int bx = dim;
   const int by = bx >= 256 ? 1 : 256 / bx;
   const dim3 block(bx, by);
   int64_t tiles = (rows + by - 1) / by;
-  const unsigned grid = (unsigned)(tiles < 1184 ? tiles : 1184);      // 8 x 148 SMs
+  const unsigned grid = (unsigned)(tiles < 2368 ? tiles : 2368);      // 16 x 148 SMs
   const size_t smem = 2ull * bx * by * sizeof(double);
   k_moments<<<grid, block, smem, (cudaStream_t)stream>>>(rows, dim, x, shift, out);
   return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;

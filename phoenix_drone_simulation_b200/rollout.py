@@ -119,12 +119,14 @@ class OnlineMeanStd:
         n_B = float(rows * _world(self.dist))
         n_A = self.count.clone()
         n_AB = self.count + n_B
-        s1, _ = self._moments(x, None)
+        # ONE pass over the batch: sum x and sum x^2 in float64; the second moment about the new mean
+        # follows as sum x^2 - 2 m sum x + rows m^2 (same value as the reference's second pass)
+        s1, s2 = self._moments(x, None)
         batch_mean = self._avg((s1 / rows).float())
         delta = batch_mean - self.mean
         mean_new = self.mean + delta * n_B / n_AB
-        _, s2 = self._moments(x, mean_new.double())
-        batch_var = self._avg((s2 / rows).float())
+        m = mean_new.double()
+        batch_var = self._avg(((s2 - 2.0 * m * s1 + rows * m * m) / rows).clamp_min(0.0).float())
         M2 = n_A * self.std ** 2 + n_B * batch_var + delta ** 2 * (n_A * n_B / n_AB)
         # in place: CUDA graphs of the policy forward hold these tensors
         self.mean.copy_(mean_new)
