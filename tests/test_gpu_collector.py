@@ -186,3 +186,43 @@ def test_policy_json_on_device_and_batched_evaluator():
     np.testing.assert_array_equal(r1, r2)
     np.testing.assert_array_equal(l1, l2)
     assert (r1 < 0).all() and (c1 >= 0).all()
+
+
+def test_simopt_objective_recovers_motor_parameters():
+    """simopt/pybullet.py:72-225 on the batched engine.  "Flight logs" come from the engine itself run
+    with known motor parameters (thrust-to-weight 1.95, motor time constant 60 ms); the objective,
+    evaluated for a grid of candidates in one fused launch, must be ~0 at the truth and minimal there."""
+    from phoenix_drone_simulation_b200 import VecEnv
+    from phoenix_drone_simulation_b200.simopt import TrajectoryObjective, euler_from_quat
+    true_t2w, true_tau, M, T, P = 1.95, 0.060, 24, 35, 5
+    kw = dict(domain_randomization=-1, observation_noise=-1, motor_thrust_noise=0.0, auto_reset=False,
+              enable_reset_distribution=False)
+    env = VecEnv('DroneHoverBulletEnv-v0', M, dtype=torch.float64, seed=1, **kw)
+    env.reset()
+    ts = env.pdx.time_step
+    env.set_state('motor_b', torch.full((M, 4), ts / true_tau, dtype=torch.float64))
+    env.set_state('motor_k', torch.full((M, 4), 0.028 * 9.81 * true_t2w / 4, dtype=torch.float64))
+    g = torch.Generator(device='cuda').manual_seed(5)
+    acts = (0.11 + 0.15 * torch.randn((P + T, M, 4), device='cuda', generator=g)).clamp(-1, 1).float()
+    logs = []
+    for t in range(P + T):
+        o, _, _, _, _ = env.step(acts[t])
+        e0 = env.core_dim + 4                                # newest history entry (H = 2) starts here
+        c = o[:, e0:e0 + 13].double()                        # noise off: xyz, quat, vel, body rates
+        logs.append(torch.cat([c[:, 0:3], c[:, 7:10], euler_from_quat(c[:, 3:7]), c[:, 10:13]], dim=1))
+    logs = torch.stack(logs, dim=1)                          # [M, P+T, 12], state AFTER step t
+    # mini-trajectory: observation 0 = state after step P-1; action i drives observation i -> i+1
+    # (the latency ring and the motor lag make the real system depend on earlier inputs, which is
+    # exactly why the reference replays pre-steps; a cleared ring leaves a small irreducible loss)
+    observations = logs[:, P - 1:P - 1 + T]
+    actions = acts[P:P + T].transpose(0, 1)
+    pre_inputs = acts[:P].transpose(0, 1)
+    obj = TrajectoryObjective(observations.cpu().numpy(), actions.cpu().numpy(), pre_inputs.cpu().numpy(),
+                              motor_thrust_noise=0.0, enable_reset_distribution=False)
+    t2ws = [1.6, 1.8, 1.95, 2.1, 2.3]
+    taus = [0.03, 0.06, 0.12]
+    cands = [(a, b) for a in t2ws for b in taus]
+    loss = obj.evaluate(cands).cpu().numpy()
+    best = cands[int(loss.argmin())]
+    assert best[0] == true_t2w, (best, loss)
+    assert np.isfinite(loss).all() and loss.min() < 0.5 * np.median(loss)
