@@ -319,6 +319,8 @@ class DistCtx:
             self.dist = dist
         else:
             self.dist = None
+        import torch as _t
+        self.episodes = _t.zeros((), dtype=_t.float64, device=self.device)   # finished episodes, all ranks
 
     def barrier(self):
         if self.dist:
@@ -338,7 +340,11 @@ class DistCtx:
         if not self.dist:
             return
         from phoenix_drone_simulation_b200.rollout import allreduce_episode_stats
-        allreduce_episode_stats(env.stats, self.dist)
+        # this segment's statistics only (the collector's flow: roll out, combine, log, clear) --
+        # re-reducing the running total in place would count every earlier segment `world` times
+        seg_stats = env.episode_stats(clear=True)
+        allreduce_episode_stats(seg_stats, self.dist)
+        self.episodes.add_(seg_stats[0])
 
     def close(self):
         if self.dist:
@@ -443,7 +449,7 @@ def run_gpu_arm(a):
             'env_steps_per_s': kl * inner_l * nl / (msl * 1e-3)}
         del big, segl
 
-    stats = env.episode_stats().cpu().tolist()
+    episodes = int(ctx.episodes.item()) if ctx.dist else int(env.episode_stats()[0].item())
     ctx.close()
     if ctx.rank != 0:
         return
@@ -452,7 +458,7 @@ def run_gpu_arm(a):
         'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a, n),
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
-        'episodes_finished': int(stats[0]),
+        'episodes_finished': episodes,
     }
     if cpu:
         line['cpu_baseline'] = cpu

@@ -224,6 +224,21 @@ int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* m
                     const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
                     uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
 
+/* The same ActorCritic.step on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators
+ * and hidden activations in tensor memory; csrc/pdx_policy_tc.cu).  128 environments per tile, one
+ * persistent CTA per SM (two for precision 1).  `precision`: 1 = operands rounded to TF32 once
+ * (~1e-3 relative error on mu / value), 3 = split-TF32 (hi + lo operands, three products per term):
+ * float32-level results.  Same Philox draws as pdx_policy_step for the same (seed, counter, env).
+ * Needs its own packed image (pdx_policy_tc_pack_words / pdx_policy_tc_pack; refresh after every
+ * weight update).  PDX_ERR_INVALID if the shapes do not fit (hidden > 64, n_out > 4, obs_dim too
+ * wide for the shared-memory plan): callers then use pdx_policy_step. */
+int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision);
+int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream);
+int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                       const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, int32_t precision,
+                       uint64_t seed, uint64_t counter, float* actions, float* values, float* logp, float* mu_out,
+                       void* stream);
+
 /* Cross-rank combination of the 8-word episode statistics (utils/mpi_tools.py:217-240 does four
  * MPI all-reduces per key): the caller all-gathers the per-rank vectors into gathered[world][8]
  * (one NCCL call) and this writes out[0..4) = sums, out[4], out[6] = minima, out[5], out[7] = maxima. */

@@ -26,6 +26,7 @@ UNITS = {
     'pdx_tu_f64_bullet_pid.cu': ['-fmad=false'],
     'pdx_abi.cu': [],
     'pdx_rollout.cu': [],
+    'pdx_policy_tc.cu': [],
 }
 
 

@@ -1,0 +1,642 @@
+// ActorCritic.step (algs/core.py:370-393) on the 5th-generation tensor cores: tcgen05.mma with the
+// accumulators -- and the hidden activations -- resident in tensor memory (TMEM).
+//
+//   standardise (utils/online_mean_std.py:42-48) -> actor MLP (relu, core.py:227-289) and critic MLP
+//   (tanh, core.py:297-310) -> a = mu + exp(log_std) * N(0,1) (Philox) -> log-probability
+//
+// One CTA works on tiles of 128 environments: environment m of the tile is TMEM lane m and row m
+// of every MMA (M = 128), so "one thread = one environment" holds for all element-wise work.
+//
+//   stage     raw observation tile (128 x D floats, contiguous in global memory) -> shared memory by
+//             ONE bulk copy of the TMA engine; threads standardise it into the canonical K-major
+//             operand layout X (tf32 hi / lo)
+//   layer 1   D1[128 x 128] = 1 * b1 + X[128 x K1] * B1   SS: X and B1 in shared memory; columns 0..63
+//                                                          actor, 64..127 critic.  The bias enters as
+//                                                          the first MMA of the chain: a constant
+//                                                          "ones" operand times a bias tile
+//   epilogue  a2 = act(D1)  written back IN PLACE into the TMEM columns of D1
+//   layer 2   D2[:, 0:64] = 1 * b2a + a2[:, 0:64] * B2a ; D2[:, 64:128] = 1 * b2c + a2[:, 64:128] * B2c
+//                                                          TS: A operand read from TMEM
+//   epilogue  a3 = act(D2)  in place
+//   layer 3   D3[128 x 16] = 1 * b3 + a3[128 x 128] * B3   TS; columns 0..3 = mu, column 4 = v
+//   epilogue  Philox draw, action, log-probability, stores
+//
+// The hidden activations never touch shared or global memory.  Every warp owns 32 TMEM lanes
+// (lane quarter w & 3) and an equal share of actor (relu) and critic (tanh) columns.  Thread 0
+// issues every tcgen05.mma and commits each layer to its own mbarrier.
+//
+// Precision: kind::tf32 keeps 10 explicit mantissa bits of each operand.  precision = 1 rounds the
+// operands once (cvt.rna.tf32) -> ~1e-3 relative error on mu / v.  precision = 3 splits both operands
+// x = hi + lo (hi = rna_tf32(x), lo = x - hi) and accumulates A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the
+// same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative): float32-level results at
+// three times the (cheap) MMA cost, which is what the parity tests pin against torch.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/phoenix_b200.h"
+
+namespace {
+
+constexpr int kTile = 128;         // environments per tile = TMEM lanes = MMA M
+constexpr int kN1 = 128;           // actor 64 | critic 64
+constexpr int kN3 = 16;
+constexpr int kB2Words = 64 * 64;
+constexpr int kB3Words = 128 * kN3;
+constexpr int kBiasTileWords = 8 * (kN1 + 64 + 64 + kN3);   // K = 8 bias tiles (row k = 0 carries the bias)
+constexpr uint32_t kLboA = 2048 + 16;   // bytes between K chunks of the X tile (+16: bank spread for the 128-bit stores)
+constexpr uint32_t kSbo = 128;          // bytes between 8-row groups: core matrices are packed
+constexpr uint32_t kOnesBytes = 2 * 2048;
+
+struct TcArgs {
+  int64_t n;
+  int32_t obs_dim, k1, act_dim, flags;
+  const float* obs;
+  const float* mean;
+  const float* std;
+  float eps;
+  const float* log_std;
+  const float* packed;
+  uint64_t seed, counter;
+  float* act; float* val; float* logp; float* mu;
+  int64_t n_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+//  PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded: a tensor-core operation that never completes (a malformed descriptor) must not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try(bar, parity); ++it)
+    if (it > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major canonical layout:
+//   element (row, k) of a 4-byte type lives at  (k / 4) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 4) * 4
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::tf32: D = f32, A = B = tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// 32 lanes x 32 bit x 16 columns: thread l of the warp gets columns [c, c+16) of lane (base lane + l)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Box-Muller on two 32-bit words with single MUFU operations (lg2, sqrt, sin, cos), the construction the
+// float32 step kernel uses (pdx_math.cuh); k_policy (pdx_rollout.cu) uses the same, so both policy kernels
+// draw identical actions for the same (seed, counter, env).
+__device__ __forceinline__ void pdx_policy_box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
+  const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));     // (0,1]
+  const float u2 = __uint_as_float(0x3f800000u | (b >> 9)) - 1.0f;     // [0,1)
+  float l2, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // -2 ln u1
+  const float ang = 6.283185307179586f * u2;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+  *z0 = r * c;
+  *z1 = r * s;
+}
+
+__device__ __forceinline__ uint4 tc_philox(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+// ---------------------------------------------------------------------------------------------
+//  Packed weight image (global == shared layout), floats:
+//    Bhi   B1[K1/4][128][4]  B2a[16][64][4]  B2c[16][64][4]  B3[32][16][4]
+//          bias tiles  Bb1[2][128][4]  Bb2a[2][64][4]  Bb2c[2][64][4]  Bb3[2][16][4]      (tf32-rounded)
+//    Blo   same shapes, w - hi                                                    (precision 3 only)
+//  B?[kc][n][j] = W[n][4 kc + j]  (torch nn.Linear weight is [out][in]): exactly the no-swizzle K-major
+//  core-matrix layout with SBO = 128 B and LBO = 16 N bytes.  Bb?[0][n][0] = bias[n], rest zero.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kB3Words + kBiasTileWords; }
+
+struct PackArgs {
+  int32_t obs_dim, k1, x3;
+  int32_t pi_h1, pi_h2, v_h1, v_h2, act_dim;
+  const float* pi_w[3]; const float* pi_b[3];
+  const float* v_w[3]; const float* v_b[3];
+  float* out;
+};
+
+__global__ void k_pack_tc(const PackArgs a) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int D = a.obs_dim, K1 = a.k1;
+  float* bhi = a.out;
+  float* blo = bhi + tc_b_words(K1);
+  const int total = (int)tc_b_words(K1);
+  for (int idx = tid; idx < total; idx += nt) {
+    float w = 0.0f;
+    int r = idx;
+    if (r < K1 * kN1) {                                   // B1: N = 128
+      const int kc = r / (kN1 * 4), n = (r / 4) % kN1, k = 4 * kc + (r & 3);
+      if (k < D) {
+        if (n < 64) { if (n < a.pi_h1) w = a.pi_w[0][n * D + k]; }
+        else if (n - 64 < a.v_h1) w = a.v_w[0][(n - 64) * D + k];
+      }
+    } else if ((r -= K1 * kN1) < 2 * kB2Words) {          // B2a, B2c: N = 64, K = 64
+      const bool critic = r >= kB2Words;
+      if (critic) r -= kB2Words;
+      const int kc = r / 256, n = (r / 4) % 64, k = 4 * kc + (r & 3);
+      const int h1 = critic ? a.v_h1 : a.pi_h1, h2 = critic ? a.v_h2 : a.pi_h2;
+      if (n < h2 && k < h1) w = (critic ? a.v_w[1] : a.pi_w[1])[n * h1 + k];
+    } else if ((r -= 2 * kB2Words) < kB3Words) {          // B3: N = 16, K = 128 (actor rows | critic rows)
+      const int kc = r / (kN3 * 4), n = (r / 4) % kN3, k = 4 * kc + (r & 3);
+      if (k < 64) { if (n < a.act_dim && k < a.pi_h2) w = a.pi_w[2][n * a.pi_h2 + k]; }
+      else if (n == 4 && k - 64 < a.v_h2) w = a.v_w[2][k - 64];
+    } else {                                              // bias tiles: only element (kc = 0, n, j = 0) is non-zero
+      r -= kB3Words;
+      if (r < 8 * kN1) {
+        const int n = r / 4;
+        if ((r & 3) == 0 && n < kN1) { if (n < 64) { if (n < a.pi_h1) w = a.pi_b[0][n]; } else if (n - 64 < a.v_h1) w = a.v_b[0][n - 64]; }
+      } else if ((r -= 8 * kN1) < 8 * 64) {
+        const int n = r / 4;
+        if ((r & 3) == 0 && n < 64 && n < a.pi_h2) w = a.pi_b[1][n];
+      } else if ((r -= 8 * 64) < 8 * 64) {
+        const int n = r / 4;
+        if ((r & 3) == 0 && n < 64 && n < a.v_h2) w = a.v_b[1][n];
+      } else {
+        r -= 8 * 64;
+        const int n = r / 4;
+        if ((r & 3) == 0 && n < kN3) { if (n < a.act_dim) w = a.pi_b[2][n]; else if (n == 4) w = a.v_b[2][0]; }
+      }
+    }
+    const float hi = __uint_as_float(tf32_rna(w));
+    bhi[idx] = hi;
+    if (a.x3) blo[idx] = w - hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+//  The kernel
+// ---------------------------------------------------------------------------------------------
+template <bool X3>
+struct TcCfg {
+  static constexpr int kThreads = X3 ? 512 : 256;      // X3: one CTA per SM (TMEM), 16 warps; else two CTAs of 8 warps
+  static constexpr int kNcg = kThreads / 128;          // column groups: warps w, w+4, ... share TMEM lane quarter w & 3
+  static constexpr int kCw = 64 / kNcg;                // columns per net and thread (16 or 32)
+  static constexpr int kTmemCols = X3 ? 512 : 256;
+  static constexpr int kMinBlocks = X3 ? 1 : 2;
+  static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256;   // TMEM column regions (R2: the lo halves, X3 only)
+  static constexpr uint32_t kD3 = X3 ? 384 : 0;        // X3: D3 has its own columns, so layer 1 of the next tile can start early
+};
+
+// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA; saturates correctly
+// (ex2 -> inf gives rcp -> 0) so no clamp is needed; ~1e-6 absolute error
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(2.885390081777927f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
+// act(D) for this thread's 2 x CW columns of one hidden layer, written back in place as the next
+// MMA's A operand (hi) and, for X3, the lo halves into region R2.
+template <bool X3>
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint32_t reg, int cg) {
+  using Cfg = TcCfg<X3>;
+#pragma unroll
+  for (int c = 0; c < Cfg::kCw / 16; ++c) {
+    const int ca = cg * Cfg::kCw + 16 * c, cc = 64 + ca;            // actor / critic column of this chunk
+    uint32_t ra[16], rc[16], la[16], lc[16];
+    tmem_ld16(taddr + reg + ca, ra);
+    tmem_ld16(taddr + reg + cc, rc);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float ya = fmaxf(__uint_as_float(ra[j]), 0.0f);
+      const float xc = __uint_as_float(rc[j]);
+      const float yc = X3 ? tanh_fast(xc) : tanh_mufu(xc);
+      ra[j] = tf32_rna(ya);
+      rc[j] = tf32_rna(yc);
+      if (X3) {
+        la[j] = __float_as_uint(ya - __uint_as_float(ra[j]));
+        lc[j] = __float_as_uint(yc - __uint_as_float(rc[j]));
+      }
+    }
+    tmem_st16(taddr + reg + ca, ra);
+    tmem_st16(taddr + reg + cc, rc);
+    if (X3) {
+      tmem_st16(taddr + Cfg::kR2 + ca, la);
+      tmem_st16(taddr + Cfg::kR2 + cc, lc);
+    }
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_policy_tc(const TcArgs a) {
+  using Cfg = TcCfg<X3>;
+  constexpr int NT = Cfg::kThreads;
+  constexpr int NB = X3 ? 2 : 1;                                           // operand images: hi (+ lo)
+  constexpr uint32_t R0 = Cfg::kR0, R1 = Cfg::kR1, R2 = Cfg::kR2, D3 = Cfg::kD3;
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.obs_dim, K1 = a.k1;
+
+  // ---- shared-memory plan
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tc_smem);                   // [0] weights [1..3] layers [4] obs tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + 40);
+  float* act_std = reinterpret_cast<float*>(tc_smem + 48);                 // exp(log_std)[4], then log_std[4]
+  float2* norm = reinterpret_cast<float2*>(tc_smem + 80);                  // [K1] (mean, 1/(std+eps))
+  uint8_t* ones = tc_smem + 80 + K1 * 8;                                   // constant A operand: column 0 = 1
+  float* bhi = reinterpret_cast<float*>(ones + kOnesBytes);
+  const int64_t bwords = tc_b_words(K1);
+  uint8_t* a1hi = reinterpret_cast<uint8_t*>(bhi + NB * bwords);
+  uint8_t* a1lo = a1hi + (K1 / 4) * kLboA;
+  float* stage = reinterpret_cast<float*>(a1hi + NB * (K1 / 4) * kLboA);   // raw observation tile [128][D]
+  const uint32_t bar_w = smem_u32(mbar), bar1 = bar_w + 8, bar2 = bar_w + 16, bar3 = bar_w + 24, bar_x = bar_w + 32;
+
+  // ---- one-time setup
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
+  if (tid == 32) {
+    mbar_init(bar_w, 1); mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); mbar_init(bar_x, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 4) {
+    const float ls = tid < a.act_dim ? a.log_std[tid] : 0.0f;
+    act_std[tid] = expf(ls);
+    act_std[4 + tid] = ls;
+  }
+  for (int k = tid; k < K1; k += NT) {
+    float m = 0.0f, inv = 1.0f;
+    if (k < D && a.std) { m = a.mean[k]; inv = 1.0f / (a.std[k] + a.eps); }
+    norm[k] = make_float2(m, inv);
+  }
+  for (int e = tid; e < (int)kOnesBytes / 4; e += NT)                       // ones[m][k]: k = 0 -> 1
+    reinterpret_cast<float*>(ones)[e] = (e < 512 && (e & 3) == 0) ? 1.0f : 0.0f;
+  const int n_chunks = (D + 3) >> 2;                                        // 16-byte K chunks that hold data
+  for (int e = tid; e < kTile * (K1 / 4 - n_chunks); e += NT) {             // K padding chunks: zero, once
+    const int m = e & (kTile - 1), kc = n_chunks + (e >> 7);
+    *reinterpret_cast<float4*>(a1hi + kc * kLboA + m * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (X3) *reinterpret_cast<float4*>(a1lo + kc * kLboA + m * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  if (tid == 0) {                                          // weight image: one bulk copy (TMA engine)
+    const uint32_t bytes = (uint32_t)(NB * bwords * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(bhi)),
+                 "l"(a.packed), "r"(bytes), "r"(bar_w)
+                 : "memory");
+  }
+
+  const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4, b3_s = b2c_s + kB2Words * 4;
+  const uint32_t bb1_s = b3_s + kB3Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4, bb3_s = bb2c_s + 8 * 64 * 4;
+  const uint32_t lo_off = (uint32_t)bwords * 4;            // Blo = Bhi + lo_off (bytes)
+  const uint32_t a1hi_s = smem_u32(a1hi), a1lo_s = smem_u32(a1lo);
+  const uint64_t ones_desc = make_desc(smem_u32(ones), 2048, kSbo);
+
+  const int q = warp & 3, cg = warp >> 2;                  // TMEM lane quarter, column group
+  const uint32_t taddr = tbase + ((uint32_t)(32 * q) << 16);
+  const int row = 32 * q + lane;                           // this thread's environment within the tile
+  const bool obs_aligned = (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0;
+
+  // raw observation tile -> `stage`: one bulk copy when the tile is full and 16-byte aligned (thread 0),
+  // otherwise (last partial tile) a cooperative copy with zero fill.  Completion is signalled on bar_x.
+  auto stage_fetch = [&](int64_t tile) {
+    const int64_t env0 = tile * kTile;
+    const bool full = (a.n - env0) >= kTile && obs_aligned;
+    if (full) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(kTile * D * 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_x), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)),
+                     "l"(a.obs + env0 * D), "r"(bytes), "r"(bar_x)
+                     : "memory");
+      }
+    } else {
+      const int n_elem = (int)(((a.n - env0) < kTile ? (a.n - env0) : kTile) * D);
+      const float* src = a.obs + env0 * D;
+      for (int e = tid; e < kTile * D; e += NT) stage[e] = e < n_elem ? __ldg(src + e) : 0.0f;
+      __syncthreads();                                     // every caller reaches this point together
+      if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_x) : "memory");
+    }
+  };
+  // `stage` -> X: standardise, split, store in the canonical K-major layout.  Sixteen lanes walk the
+  // 16-byte K chunks of one environment row (contiguous shared-memory reads), two rows per warp.
+  auto stage_to_x = [&]() {
+    const int kc = tid & 15;
+    if (kc < n_chunks) {
+#pragma unroll 2
+      for (int m = tid >> 4; m < kTile; m += NT / 16) {
+        const float* src = stage + m * D + 4 * kc;
+        uint32_t hi[4];
+        float lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = 0.0f;
+          if (4 * kc + j < D) {
+            const float2 nm = norm[4 * kc + j];
+            x = (src[j] - nm.x) * nm.y;
+          }
+          hi[j] = tf32_rna(x);
+          lo[j] = x - __uint_as_float(hi[j]);
+        }
+        *reinterpret_cast<uint4*>(a1hi + kc * kLboA + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (X3) *reinterpret_cast<float4*>(a1lo + kc * kLboA + m * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  };
+  auto issue_layer1 = [&]() {                              // thread 0 only
+    constexpr uint32_t idesc = make_idesc(kN1);
+    const uint32_t lbo_b = kN1 * 16;
+    mma_ss(tbase + R0, ones_desc, make_desc(bb1_s, lbo_b, kSbo), idesc, 0);
+    if (X3) mma_ss(tbase + R0, ones_desc, make_desc(bb1_s + lo_off, lbo_b, kSbo), idesc, 1);
+    for (int ks = 0; ks < K1 / 8; ++ks) {
+      const uint64_t ah = make_desc(a1hi_s + ks * 2 * kLboA, kLboA, kSbo), bh = make_desc(b1_s + ks * 2 * lbo_b, lbo_b, kSbo);
+      if (X3) {
+        const uint64_t al = make_desc(a1lo_s + ks * 2 * kLboA, kLboA, kSbo);
+        const uint64_t bl = make_desc(b1_s + lo_off + ks * 2 * lbo_b, lbo_b, kSbo);
+        mma_ss(tbase + R0, al, bh, idesc, 1);
+        mma_ss(tbase + R0, ah, bl, idesc, 1);
+      }
+      mma_ss(tbase + R0, ah, bh, idesc, 1);
+    }
+    tc_commit(bar1);
+  };
+
+  // ---- prologue: first tile
+  int64_t tile = blockIdx.x;
+  stage_fetch(tile);
+  mbar_wait(bar_x, 0);
+  stage_to_x();
+  mbar_wait(bar_w, 0);               // weight image landed (async-proxy writes, visible after the wait)
+  fence_async_smem();                // generic-proxy writes of X / ones -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    issue_layer1();
+  }
+  if (tile + gridDim.x < a.n_tiles) stage_fetch(tile + gridDim.x);          // `stage` was consumed before the barrier
+
+  uint32_t par = 0;
+  for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1) {
+    const int64_t env0 = tile * kTile;
+    const int64_t next = tile + gridDim.x;
+    const bool has_next = next < a.n_tiles;
+    // ---- layer 1 done -> activation in place
+    mbar_wait(bar1, par);
+    tc_fence_after();
+    hidden_epilogue<X3>(taddr, R0, cg);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(64);
+      const uint32_t lbo_b = 64 * 16;
+      for (int net = 0; net < 2; ++net) {
+        const uint32_t bs = net ? b2c_s : b2a_s, bbs = net ? bb2c_s : bb2a_s;
+        const uint32_t d = tbase + R1 + 64 * net, ahi = tbase + R0 + 64 * net, alo = tbase + R2 + 64 * net;
+        mma_ss(d, ones_desc, make_desc(bbs, lbo_b, kSbo), idesc, 0);
+        if (X3) mma_ss(d, ones_desc, make_desc(bbs + lo_off, lbo_b, kSbo), idesc, 1);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t bh = make_desc(bs + ks * 2 * lbo_b, lbo_b, kSbo);
+          if (X3) {
+            mma_ts(d, alo + ks * 8, bh, idesc, 1);
+            mma_ts(d, ahi + ks * 8, make_desc(bs + lo_off + ks * 2 * lbo_b, lbo_b, kSbo), idesc, 1);
+          }
+          mma_ts(d, ahi + ks * 8, bh, idesc, 1);
+        }
+      }
+      tc_commit(bar2);
+    }
+    // ---- while layer 2 runs: the next tile's observations (already in `stage`) -> X (layer 1 of this
+    // tile has completed, so the X buffer is free)
+    if (has_next) {
+      mbar_wait(bar_x, par ^ 1);
+      stage_to_x();
+    }
+    // ---- layer 2 done -> activation in place
+    mbar_wait(bar2, par);
+    tc_fence_after();
+    hidden_epilogue<X3>(taddr, R1, cg);
+    tmem_wait_st();
+    fence_async_smem();               // X of the next tile -> async proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(kN3);
+      const uint32_t lbo_b = kN3 * 16;
+      mma_ss(tbase + D3, ones_desc, make_desc(bb3_s, lbo_b, kSbo), idesc, 0);
+      if (X3) mma_ss(tbase + D3, ones_desc, make_desc(bb3_s + lo_off, lbo_b, kSbo), idesc, 1);
+      for (int ks = 0; ks < 16; ++ks) {
+        const uint64_t bh = make_desc(b3_s + ks * 2 * lbo_b, lbo_b, kSbo);
+        if (X3) {
+          mma_ts(tbase + D3, tbase + R2 + ks * 8, bh, idesc, 1);
+          mma_ts(tbase + D3, tbase + R1 + ks * 8, make_desc(b3_s + lo_off + ks * 2 * lbo_b, lbo_b, kSbo), idesc, 1);
+        }
+        mma_ts(tbase + D3, tbase + R1 + ks * 8, bh, idesc, 1);
+      }
+      tc_commit(bar3);
+      if (X3 && has_next) issue_layer1();                 // D3 has its own columns: start the next tile now
+    }
+    if (next + gridDim.x < a.n_tiles) stage_fetch(next + gridDim.x);        // `stage` is free again
+    // ---- output layer: mu (columns 0..3), v (column 4); sample, log-probability, stores
+    mbar_wait(bar3, par);
+    tc_fence_after();
+    if (cg == 0) {
+      uint32_t r[16];
+      tmem_ld16(taddr + D3, r);
+      tmem_wait_ld();
+      const int64_t i = env0 + row;
+      if (i < a.n) {
+        // same Philox counters as k_policy: identical draws for the same (seed, counter, env)
+        const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        float eps[4];
+        pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
+        pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
+        float lp = 0.0f;
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, mu[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mu[k] = __uint_as_float(r[k]);
+          if (k < a.act_dim) {
+            av[k] = fmaf(act_std[k], eps[k], mu[k]);
+            lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
+          }
+        }
+        reinterpret_cast<float4*>(a.act)[i] = make_float4(av[0], av[1], av[2], av[3]);
+        a.val[i] = __uint_as_float(r[4]);
+        a.logp[i] = lp;
+        if (a.mu) reinterpret_cast<float4*>(a.mu)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+      }
+    }
+    if (!X3 && has_next) {            // D3 shares columns with D1: wait for the readers, then layer 1 of the next tile
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_layer1();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free<Cfg::kTmemCols>(tbase);
+}
+
+size_t tc_smem_bytes(int k1, int obs_dim, bool x3) {
+  const size_t nb = x3 ? 2 : 1;
+  return 80 + (size_t)k1 * 8 + kOnesBytes + nb * tc_b_words(k1) * 4 + nb * (k1 / 4) * kLboA + (size_t)kTile * obs_dim * 4;
+}
+
+int tc_select_device_of(const void* ptr) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PDX_ERR_NO_DEVICE;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return PDX_ERR_INVALID;
+  }
+  return cudaSetDevice(attr.device) == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+}
+
+bool tc_shapes_ok(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
+  if (obs_dim <= 0 || !pi || !v || (precision != 1 && precision != 3)) return false;
+  if (pi->hidden[0] < 1 || pi->hidden[0] > 64 || pi->hidden[1] < 1 || pi->hidden[1] > 64 || pi->n_out < 1 || pi->n_out > 4) return false;
+  if (v->hidden[0] < 1 || v->hidden[0] > 64 || v->hidden[1] < 1 || v->hidden[1] > 64 || v->n_out != 1) return false;
+  const int k1 = (obs_dim + 7) & ~7;
+  if (k1 > 64) return false;                              // sixteen lanes walk the K chunks of a row (stage_to_x)
+  return tc_smem_bytes(k1, obs_dim, precision == 3) <= (size_t)227 * 1024;
+}
+
+}  // namespace
+
+extern "C" int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
+  if (!tc_shapes_ok(obs_dim, pi, v, precision)) return PDX_ERR_INVALID;
+  const int k1 = (obs_dim + 7) & ~7;
+  return (precision == 3 ? 2 : 1) * tc_b_words(k1);
+}
+
+extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream) {
+  if (!packed || !tc_shapes_ok(obs_dim, pi, v, precision)) return PDX_ERR_INVALID;
+  const int rc = tc_select_device_of(packed);
+  if (rc) return rc;
+  PackArgs p;
+  p.obs_dim = obs_dim; p.k1 = (obs_dim + 7) & ~7; p.x3 = precision == 3;
+  p.pi_h1 = pi->hidden[0]; p.pi_h2 = pi->hidden[1]; p.v_h1 = v->hidden[0]; p.v_h2 = v->hidden[1]; p.act_dim = pi->n_out;
+  for (int k = 0; k < 3; ++k) { p.pi_w[k] = pi->weight[k]; p.pi_b[k] = pi->bias[k]; p.v_w[k] = v->weight[k]; p.v_b[k] = v->bias[k]; }
+  p.out = packed;
+  k_pack_tc<<<16, 256, 0, (cudaStream_t)stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+}
+
+extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
+                                  const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, int32_t precision,
+                                  uint64_t seed, uint64_t counter, float* actions, float* values, float* logp, float* mu_out,
+                                  void* stream) {
+  if (n <= 0 || !obs || !log_std || !packed || !actions || !values || !logp || !tc_shapes_ok(obs_dim, pi, v, precision))
+    return PDX_ERR_INVALID;
+  const int rc = tc_select_device_of(obs);
+  if (rc) return rc;
+  const bool x3 = precision == 3;
+  TcArgs a;
+  a.n = n; a.obs_dim = obs_dim; a.k1 = (obs_dim + 7) & ~7; a.act_dim = pi->n_out;
+  a.flags = 0;
+  a.obs = obs; a.mean = mean; a.std = std; a.eps = eps; a.log_std = log_std; a.packed = packed;
+  a.seed = seed; a.counter = counter; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
+  a.n_tiles = (n + kTile - 1) / kTile;
+  const size_t smem = tc_smem_bytes(a.k1, obs_dim, x3);
+  static size_t set[2] = {0, 0};
+  if (smem > set[x3]) {
+    const cudaError_t e = x3 ? cudaFuncSetAttribute(k_policy_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_policy_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return PDX_ERR_CUDA;
+    set[x3] = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent CTAs: TMEM (512 columns per SM) admits one precision-3 CTA or two precision-1 CTAs per SM
+  const int64_t resident = (int64_t)sms * (x3 ? 1 : ((size_t)2 * smem <= (size_t)227 * 1024 ? 2 : 1));
+  const unsigned grid = (unsigned)(a.n_tiles < resident ? a.n_tiles : resident);
+  if (x3) k_policy_tc<true><<<grid, TcCfg<true>::kThreads, smem, (cudaStream_t)stream>>>(a);
+  else k_policy_tc<false><<<grid, TcCfg<false>::kThreads, smem, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+}

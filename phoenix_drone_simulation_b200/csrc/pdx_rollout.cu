@@ -277,16 +277,23 @@ __global__ void __launch_bounds__(kPolBlock) k_policy(const PolArgs a) {
   // ---- sample: a = mu + std * eps, log p = sum(-eps^2/2 - log_std - log(2 pi)/2)
   const uint4 r = pol_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
                              make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+  // Box-Muller with single MUFU operations (lg2, sqrt, sin, cos) -- the construction of the float32 step
+  // kernel (pdx_math.cuh) and of k_policy_tc, so both policy kernels draw identical actions
   float eps[4];
+  {
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const float u1 = ((float)(rw[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = ((float)(rw[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincosf(6.283185307179586f * u2, &s, &c);
-    eps[2 * p] = rad * c; eps[2 * p + 1] = rad * s;
+    for (int p = 0; p < 2; ++p) {
+      const float u1 = 2.0f - __uint_as_float(0x3f800000u | (rw[2 * p] >> 9));       // (0,1]
+      const float u2 = __uint_as_float(0x3f800000u | (rw[2 * p + 1] >> 9)) - 1.0f;   // [0,1)
+      float l2, rad, sn, cs;
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * l2));
+      const float ang = 6.283185307179586f * u2;
+      asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+      asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+      eps[2 * p] = rad * cs; eps[2 * p + 1] = rad * sn;
+    }
   }
   float lp = 0.0f;
   float4 act = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -177,8 +177,13 @@ def _mlp(sizes, act):
 
 class ActorCritic(torch.nn.Module):
     def __init__(self, obs_dim, act_dim=4, pi_hidden=(50, 50), v_hidden=(64, 64), device='cuda',
-                 use_standardized_obs=True, use_scaled_rewards=True, dist=None, fused=True, seed=0):
+                 use_standardized_obs=True, use_scaled_rewards=True, dist=None, fused=True, seed=0,
+                 policy_kernel='tc'):
         super().__init__()
+        # policy_kernel: 'tc' = tcgen05 tensor-core kernel, split-TF32 operands (float32-level results);
+        # 'tc_tf32' = the same with operands rounded to TF32 once (~1e-3 relative error on mu / value);
+        # 'cuda' = the CUDA-core float32 kernel (also the fallback for shapes the tensor-core plan rejects)
+        self.tc_precision = {'tc': 3, 'tc_tf32': 1, 'cuda': 0}[policy_kernel]
         # fused: one CUDA kernel (pdx_policy_step) does standardise + both MLPs + sample + log-prob;
         # the torch modules below stay the owners of the weights (training updates them in place)
         self.fused = (fused and len(pi_hidden) == 2 and len(v_hidden) == 2 and max(*pi_hidden, *v_hidden) <= 64
@@ -214,14 +219,29 @@ class ActorCritic(torch.nn.Module):
         """Device blob of the transposed / padded weights, re-packed when a parameter changed
         (torch bumps `_version` on every in-place update)."""
         params = [p_ for net in (self.pi, self.v) for p_ in net.parameters()]
-        ver = tuple(p_._version for p_ in params) + tuple(p_.data_ptr() for p_ in params)
+        L = _lib.load()
+        prec = self.tc_precision
+        if prec and int(L.pdx_policy_tc_pack_words(obs_dim, C.byref(pi), C.byref(v), prec)) < 0:
+            prec = self.tc_precision = 0                  # shapes outside the tensor-core plan
+        ver = tuple(p_._version for p_ in params) + tuple(p_.data_ptr() for p_ in params) + (prec,)
         if getattr(self, '_pack_ver', None) != ver:
-            words = int(_lib.load().pdx_policy_pack_words(obs_dim, C.byref(pi), C.byref(v)))
+            words = int(L.pdx_policy_tc_pack_words(obs_dim, C.byref(pi), C.byref(v), prec) if prec
+                        else L.pdx_policy_pack_words(obs_dim, C.byref(pi), C.byref(v)))
             if getattr(self, '_pack', None) is None or self._pack.numel() != words:
                 self._pack = torch.empty(words, dtype=torch.float32, device=params[0].device)
-            _lib.check(_lib.load().pdx_policy_pack(obs_dim, C.byref(pi), C.byref(v), C.c_void_p(self._pack.data_ptr()), stream))
+            if prec:
+                _lib.check(L.pdx_policy_tc_pack(obs_dim, C.byref(pi), C.byref(v), prec, C.c_void_p(self._pack.data_ptr()), stream))
+            else:
+                _lib.check(L.pdx_policy_pack(obs_dim, C.byref(pi), C.byref(v), C.c_void_p(self._pack.data_ptr()), stream))
             self._pack_ver = ver
         return self._pack
+
+    def _launch_policy(self, head, counter, tail, stream):
+        """head = (n, d, obs, mean, std, eps, pi, v, log_std, pack, seed); tail = (act, val, logp, mu)."""
+        L = _lib.load()
+        if self.tc_precision:
+            return L.pdx_policy_step_tc(*head[:10], self.tc_precision, head[10], counter, *tail, stream)
+        return L.pdx_policy_step(*head, counter, *tail, stream)
 
     @torch.no_grad()
     def step_into(self, obs, act, val, logp, mu=None):
@@ -238,9 +258,9 @@ class ActorCritic(torch.nn.Module):
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         st = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         pack = self._packed_weights(d, pi, v, st)
-        _lib.check(_lib.load().pdx_policy_step(n, d, p(obs), p(oms.mean) if oms else None, p(oms.std) if oms else None,
-                                               oms.eps if oms else 0.0, C.byref(pi), C.byref(v), p(self.log_std.data),
-                                               p(pack), self.seed, self._counter, p(act), p(val), p(logp), p(mu), st))
+        head = (n, d, p(obs), p(oms.mean) if oms else None, p(oms.std) if oms else None, oms.eps if oms else 0.0,
+                C.byref(pi), C.byref(v), p(self.log_std.data), p(pack), self.seed)
+        _lib.check(self._launch_policy(head, self._counter, (p(act), p(val), p(logp), p(mu)), st))
 
     def prepare_step_into(self, obs, act, val, logp):
         """Handle for `step_prepared`: all ctypes arguments of one fused policy step, built once.
@@ -263,13 +283,9 @@ class ActorCritic(torch.nn.Module):
 
     def step_prepared(self, handle, stream):
         self._counter += 1
-        rc = self._lib_policy(*handle[0], self._counter, *handle[1], stream)
+        rc = self._launch_policy(handle[0], self._counter, handle[1], stream)
         if rc:
             _lib.check(rc)
-
-    @property
-    def _lib_policy(self):
-        return _lib.load().pdx_policy_step
 
     @torch.no_grad()
     def step(self, obs, generator=None):

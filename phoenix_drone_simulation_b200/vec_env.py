@@ -288,7 +288,10 @@ class VecEnv:
 
     # ---- episode statistics (block-reduced in the step kernel) ------------------------------
     def clear_episode_stats(self):
-        self.stats.copy_(torch.tensor([0., 0., 0., 0., 1e300, -1e300, 1e300, -1e300], dtype=torch.float64))
+        if getattr(self, '_stats_init', None) is None:       # device-resident constant: no H2D copy per clear
+            self._stats_init = torch.tensor([0., 0., 0., 0., 1e300, -1e300, 1e300, -1e300], dtype=torch.float64,
+                                            device=self.stats.device)
+        self.stats.copy_(self._stats_init)
 
     def episode_stats(self, clear=False):
         """[n, sum ret, sum ret^2, sum len, min ret, max ret, min len, max len] (float64)."""
