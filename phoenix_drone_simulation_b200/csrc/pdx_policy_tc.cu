@@ -16,18 +16,22 @@
 //                                                          "ones" operand times a bias tile
 //   epilogue  a2 = act(D1)  written back IN PLACE into the TMEM columns of D1
 //   layer 2   D2[:, 0:64] = 1 * b2a + a2[:, 0:64] * B2a ; D2[:, 64:128] = 1 * b2c + a2[:, 64:128] * B2c
-//                                                          TS: A operand read from TMEM
-//   epilogue  a3 = act(D2)  in place
-//   layer 3   D3[128 x 16] = 1 * b3 + a3[128 x 128] * B3   TS; columns 0..3 = mu, column 4 = v
-//   epilogue  Philox draw, action, log-probability, stores
+//                                                          TS: A operand read from TMEM.  Independent
+//                                                          accumulators (actor / critic, and for the
+//                                                          split mode two K halves each) are issued
+//                                                          interleaved: a chain of MMAs into ONE
+//                                                          accumulator runs at the MMA latency
+//   epilogue  a3 = act(D2) stays in registers; layer 3 (64 x 4 + 64 x 1 weights) is a dot product on
+//             the CUDA cores in float32 -- each thread covers its columns, partial sums meet in
+//             shared memory -- then Philox draw, action, log-probability, stores
 //
 // The hidden activations never touch shared or global memory.  Every warp owns 32 TMEM lanes
 // (lane quarter w & 3) and an equal share of actor (relu) and critic (tanh) columns.  Thread 0
 // issues every tcgen05.mma and commits each layer to its own mbarrier.
 //
 // Precision: kind::tf32 keeps 10 explicit mantissa bits of each operand.  precision = 1 rounds the
-// operands once (cvt.rna.tf32) -> ~1e-3 relative error on mu / v.  precision = 3 splits both operands
-// x = hi + lo (hi = rna_tf32(x), lo = x - hi) and accumulates A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the
+// operands once (to nearest) -> ~1e-3 relative error on mu / v.  precision = 3 splits both operands
+// x = hi + lo (hi = tf32(x), lo = x - hi) and accumulates A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the
 // same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative): float32-level results at
 // three times the (cheap) MMA cost, which is what the parity tests pin against torch.
 #include <cuda_runtime.h>
@@ -38,10 +42,9 @@ namespace {
 
 constexpr int kTile = 128;         // environments per tile = TMEM lanes = MMA M
 constexpr int kN1 = 128;           // actor 64 | critic 64
-constexpr int kN3 = 16;
 constexpr int kB2Words = 64 * 64;
-constexpr int kB3Words = 128 * kN3;
-constexpr int kBiasTileWords = 8 * (kN1 + 64 + 64 + kN3);   // K = 8 bias tiles (row k = 0 carries the bias)
+constexpr int kBiasTileWords = 8 * (kN1 + 64 + 64);     // K = 8 bias tiles (row k = 0 carries the bias)
+constexpr int kCommonWords = 64 * 4 + 64 + 16;          // float32 layer 3: w3a[64][4], w3c[64], b3[16]
 constexpr uint32_t kLboA = 2048 + 16;   // bytes between K chunks of the X tile (+16: bank spread for the 128-bit stores)
 constexpr uint32_t kSbo = 128;          // bytes between 8-row groups: core matrices are packed
 constexpr uint32_t kOnesBytes = 2 * 2048;
@@ -80,9 +83,15 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded: a tensor-core operation that never completes (a malformed descriptor) must not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_thread(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try(bar, parity); ++it)
     if (it > (1u << 24)) __trap();
+}
+// warp-level wait: ONE lane polls (32 lanes hitting the same mbarrier word serialise), the warp
+// re-converges on __syncwarp, which also orders the other lanes' later reads after the acquire
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_thread(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -97,8 +106,11 @@ template <int COLS>
 __device__ __forceinline__ void tmem_free(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar) {            // warp-uniform call, elected lane commits
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
 }
 
 // shared-memory matrix descriptor, no swizzle, K-major canonical layout:
@@ -111,16 +123,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 }
 
+// Called by ALL lanes of the issuing warp with warp-uniform operands (they then live in uniform registers);
+// elect.sync picks one lane and only the tcgen05 instruction itself is predicated on it.
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 
@@ -143,11 +157,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
-}
+// round to nearest (ties away) onto the 10 explicit mantissa bits of tf32: two integer operations
+// (cvt.rna.tf32.f32 expands to an eight-instruction sequence with special-value handling)
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ float tanh_mufu(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -183,13 +195,14 @@ __device__ __forceinline__ uint4 tc_philox(uint4 ctr, uint2 key) {
 
 // ---------------------------------------------------------------------------------------------
 //  Packed weight image (global == shared layout), floats:
-//    Bhi   B1[K1/4][128][4]  B2a[16][64][4]  B2c[16][64][4]  B3[32][16][4]
-//          bias tiles  Bb1[2][128][4]  Bb2a[2][64][4]  Bb2c[2][64][4]  Bb3[2][16][4]      (tf32-rounded)
-//    Blo   same shapes, w - hi                                                    (precision 3 only)
+//    common  w3a[64][4] (actor output weights, [hidden][action]), w3c[64] (critic), b3[16] (mu biases 0..3, v bias 4)
+//    Bhi     B1[K1/4][128][4]  B2a[16][64][4]  B2c[16][64][4]
+//            bias tiles  Bb1[2][128][4]  Bb2a[2][64][4]  Bb2c[2][64][4]                  (tf32-rounded)
+//    Blo     same shapes, w - hi                                                  (precision 3 only)
 //  B?[kc][n][j] = W[n][4 kc + j]  (torch nn.Linear weight is [out][in]): exactly the no-swizzle K-major
 //  core-matrix layout with SBO = 128 B and LBO = 16 N bytes.  Bb?[0][n][0] = bias[n], rest zero.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kB3Words + kBiasTileWords; }
+__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kBiasTileWords; }
 
 struct PackArgs {
   int32_t obs_dim, k1, x3;
@@ -202,8 +215,17 @@ struct PackArgs {
 __global__ void k_pack_tc(const PackArgs a) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int D = a.obs_dim, K1 = a.k1;
-  float* bhi = a.out;
+  float* common = a.out;
+  float* bhi = common + kCommonWords;
   float* blo = bhi + tc_b_words(K1);
+  for (int j = tid; j < kCommonWords; j += nt) {
+    float w = 0.0f;
+    if (j < 256) { const int k = j >> 2, o = j & 3; if (k < a.pi_h2 && o < a.act_dim) w = a.pi_w[2][o * a.pi_h2 + k]; }
+    else if (j < 320) { if (j - 256 < a.v_h2) w = a.v_w[2][j - 256]; }
+    else if (j - 320 < a.act_dim) w = a.pi_b[2][j - 320];
+    else if (j - 320 == 4) w = a.v_b[2][0];
+    common[j] = w;
+  }
   const int total = (int)tc_b_words(K1);
   for (int idx = tid; idx < total; idx += nt) {
     float w = 0.0f;
@@ -220,25 +242,18 @@ __global__ void k_pack_tc(const PackArgs a) {
       const int kc = r / 256, n = (r / 4) % 64, k = 4 * kc + (r & 3);
       const int h1 = critic ? a.v_h1 : a.pi_h1, h2 = critic ? a.v_h2 : a.pi_h2;
       if (n < h2 && k < h1) w = (critic ? a.v_w[1] : a.pi_w[1])[n * h1 + k];
-    } else if ((r -= 2 * kB2Words) < kB3Words) {          // B3: N = 16, K = 128 (actor rows | critic rows)
-      const int kc = r / (kN3 * 4), n = (r / 4) % kN3, k = 4 * kc + (r & 3);
-      if (k < 64) { if (n < a.act_dim && k < a.pi_h2) w = a.pi_w[2][n * a.pi_h2 + k]; }
-      else if (n == 4 && k - 64 < a.v_h2) w = a.v_w[2][k - 64];
     } else {                                              // bias tiles: only element (kc = 0, n, j = 0) is non-zero
-      r -= kB3Words;
+      r -= 2 * kB2Words;
       if (r < 8 * kN1) {
         const int n = r / 4;
         if ((r & 3) == 0 && n < kN1) { if (n < 64) { if (n < a.pi_h1) w = a.pi_b[0][n]; } else if (n - 64 < a.v_h1) w = a.v_b[0][n - 64]; }
       } else if ((r -= 8 * kN1) < 8 * 64) {
         const int n = r / 4;
         if ((r & 3) == 0 && n < 64 && n < a.pi_h2) w = a.pi_b[1][n];
-      } else if ((r -= 8 * 64) < 8 * 64) {
-        const int n = r / 4;
-        if ((r & 3) == 0 && n < 64 && n < a.v_h2) w = a.v_b[1][n];
       } else {
         r -= 8 * 64;
         const int n = r / 4;
-        if ((r & 3) == 0 && n < kN3) { if (n < a.act_dim) w = a.pi_b[2][n]; else if (n == 4) w = a.v_b[2][0]; }
+        if ((r & 3) == 0 && n < 64 && n < a.v_h2) w = a.v_b[1][n];
       }
     }
     const float hi = __uint_as_float(tf32_rna(w));
@@ -250,6 +265,13 @@ __global__ void k_pack_tc(const PackArgs a) {
 // ---------------------------------------------------------------------------------------------
 //  The kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef PDX_TC_TIMING
+__device__ long long tc_timing[16 * 8];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0 && tid == 64 && tcount < 8) tc_timing[tcount * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#endif
+
 template <bool X3>
 struct TcCfg {
   static constexpr int kThreads = X3 ? 512 : 256;      // X3: one CTA per SM (TMEM), 16 warps; else two CTAs of 8 warps
@@ -257,8 +279,9 @@ struct TcCfg {
   static constexpr int kCw = 64 / kNcg;                // columns per net and thread (16 or 32)
   static constexpr int kTmemCols = X3 ? 512 : 256;
   static constexpr int kMinBlocks = X3 ? 1 : 2;
-  static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256;   // TMEM column regions (R2: the lo halves, X3 only)
-  static constexpr uint32_t kD3 = X3 ? 384 : 0;        // X3: D3 has its own columns, so layer 1 of the next tile can start early
+  static constexpr int kSplit = 1;                     // layer-2 accumulators per net (2 = K halves summed in the epilogue: no gain measured)
+  // TMEM column regions: R0 = D1 -> a2 (hi), R1 = D2 (first K half), R2 = a2 lo, R3 = D2 (second K half)
+  static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256, kR3 = 384;
 };
 
 // tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA; saturates correctly
@@ -270,17 +293,17 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, r, 1.0f);
 }
 
-// act(D) for this thread's 2 x CW columns of one hidden layer, written back in place as the next
-// MMA's A operand (hi) and, for X3, the lo halves into region R2.
+// a2 = act(D1) for this thread's 2 x CW columns, written back in place as layer 2's A operand (hi) and,
+// for X3, the lo halves into region R2.
 template <bool X3>
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint32_t reg, int cg) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int cg) {
   using Cfg = TcCfg<X3>;
 #pragma unroll
   for (int c = 0; c < Cfg::kCw / 16; ++c) {
     const int ca = cg * Cfg::kCw + 16 * c, cc = 64 + ca;            // actor / critic column of this chunk
     uint32_t ra[16], rc[16], la[16], lc[16];
-    tmem_ld16(taddr + reg + ca, ra);
-    tmem_ld16(taddr + reg + cc, rc);
+    tmem_ld16(taddr + Cfg::kR0 + ca, ra);
+    tmem_ld16(taddr + Cfg::kR0 + cc, rc);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -294,11 +317,53 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint32_t reg, in
         lc[j] = __float_as_uint(yc - __uint_as_float(rc[j]));
       }
     }
-    tmem_st16(taddr + reg + ca, ra);
-    tmem_st16(taddr + reg + cc, rc);
+    tmem_st16(taddr + Cfg::kR0 + ca, ra);
+    tmem_st16(taddr + Cfg::kR0 + cc, rc);
     if (X3) {
       tmem_st16(taddr + Cfg::kR2 + ca, la);
       tmem_st16(taddr + Cfg::kR2 + cc, lc);
+    }
+  }
+}
+
+// a3 = act(D2) for this thread's columns and its share of layer 3 in float32:
+// part[0..3] += a3_actor[col] * w3a[col][0..3], part[4] += a3_critic[col] * w3c[col]
+template <bool X3>
+__device__ __forceinline__ void output_epilogue(uint32_t taddr, int cg, const float* __restrict__ w3a,
+                                                const float* __restrict__ w3c, float (&part)[5]) {
+  using Cfg = TcCfg<X3>;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) part[k] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < Cfg::kCw / 16; ++c) {
+    const int ca = cg * Cfg::kCw + 16 * c, cc = 64 + ca;
+    uint32_t ra[16], rc[16];
+    tmem_ld16(taddr + Cfg::kR1 + ca, ra);
+    tmem_ld16(taddr + Cfg::kR1 + cc, rc);
+    if (Cfg::kSplit == 2) {
+      uint32_t sa[16], sc[16];
+      tmem_ld16(taddr + Cfg::kR3 + ca, sa);
+      tmem_ld16(taddr + Cfg::kR3 + cc, sc);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(sa[j]));
+        rc[j] = __float_as_uint(__uint_as_float(rc[j]) + __uint_as_float(sc[j]));
+      }
+    } else {
+      tmem_wait_ld();
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float ya = fmaxf(__uint_as_float(ra[j]), 0.0f);
+      const float xc = __uint_as_float(rc[j]);
+      const float yc = X3 ? tanh_fast(xc) : tanh_mufu(xc);
+      const float4 w = *reinterpret_cast<const float4*>(w3a + 4 * (ca + j));
+      part[0] = fmaf(ya, w.x, part[0]);
+      part[1] = fmaf(ya, w.y, part[1]);
+      part[2] = fmaf(ya, w.z, part[2]);
+      part[3] = fmaf(ya, w.w, part[3]);
+      part[4] = fmaf(yc, w3c[ca + j], part[4]);
     }
   }
 }
@@ -308,28 +373,30 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
   using Cfg = TcCfg<X3>;
   constexpr int NT = Cfg::kThreads;
   constexpr int NB = X3 ? 2 : 1;                                           // operand images: hi (+ lo)
-  constexpr uint32_t R0 = Cfg::kR0, R1 = Cfg::kR1, R2 = Cfg::kR2, D3 = Cfg::kD3;
+  constexpr uint32_t R0 = Cfg::kR0, R1 = Cfg::kR1, R2 = Cfg::kR2, R3 = Cfg::kR3;
   extern __shared__ __align__(128) uint8_t tc_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = a.obs_dim, K1 = a.k1;
 
   // ---- shared-memory plan
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tc_smem);                   // [0] weights [1..3] layers [4] obs tile
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tc_smem);                   // [0] weights [1..2] layers [3] obs tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + 40);
   float* act_std = reinterpret_cast<float*>(tc_smem + 48);                 // exp(log_std)[4], then log_std[4]
   float2* norm = reinterpret_cast<float2*>(tc_smem + 80);                  // [K1] (mean, 1/(std+eps))
   uint8_t* ones = tc_smem + 80 + K1 * 8;                                   // constant A operand: column 0 = 1
-  float* bhi = reinterpret_cast<float*>(ones + kOnesBytes);
+  float* part_sm = reinterpret_cast<float*>(ones + kOnesBytes);            // [kNcg][128][8] layer-3 partial sums
+  float* common = part_sm + Cfg::kNcg * kTile * 8;                         // w3a, w3c, b3 (start of the weight image)
+  float* bhi = common + kCommonWords;
   const int64_t bwords = tc_b_words(K1);
   uint8_t* a1hi = reinterpret_cast<uint8_t*>(bhi + NB * bwords);
   uint8_t* a1lo = a1hi + (K1 / 4) * kLboA;
   float* stage = reinterpret_cast<float*>(a1hi + NB * (K1 / 4) * kLboA);   // raw observation tile [128][D]
-  const uint32_t bar_w = smem_u32(mbar), bar1 = bar_w + 8, bar2 = bar_w + 16, bar3 = bar_w + 24, bar_x = bar_w + 32;
+  const uint32_t bar_w = smem_u32(mbar), bar1 = bar_w + 8, bar2 = bar_w + 16, bar_x = bar_w + 24;
 
   // ---- one-time setup
   if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   if (tid == 32) {
-    mbar_init(bar_w, 1); mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); mbar_init(bar_x, 1);
+    mbar_init(bar_w, 1); mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar_x, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 4) {
@@ -355,15 +422,15 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   if (tid == 0) {                                          // weight image: one bulk copy (TMA engine)
-    const uint32_t bytes = (uint32_t)(NB * bwords * 4);
+    const uint32_t bytes = (uint32_t)((kCommonWords + NB * bwords) * 4);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(bhi)),
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(common)),
                  "l"(a.packed), "r"(bytes), "r"(bar_w)
                  : "memory");
   }
 
-  const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4, b3_s = b2c_s + kB2Words * 4;
-  const uint32_t bb1_s = b3_s + kB3Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4, bb3_s = bb2c_s + 8 * 64 * 4;
+  const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4;
+  const uint32_t bb1_s = b2c_s + kB2Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4;
   const uint32_t lo_off = (uint32_t)bwords * 4;            // Blo = Bhi + lo_off (bytes)
   const uint32_t a1hi_s = smem_u32(a1hi), a1lo_s = smem_u32(a1lo);
   const uint64_t ones_desc = make_desc(smem_u32(ones), 2048, kSbo);
@@ -399,18 +466,17 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
   auto stage_to_x = [&]() {
     const int kc = tid & 15;
     if (kc < n_chunks) {
-#pragma unroll 2
+      float2 nm[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nm[j] = 4 * kc + j < D ? norm[4 * kc + j] : make_float2(0.0f, 0.0f);
+#pragma unroll 4
       for (int m = tid >> 4; m < kTile; m += NT / 16) {
         const float* src = stage + m * D + 4 * kc;
         uint32_t hi[4];
         float lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float x = 0.0f;
-          if (4 * kc + j < D) {
-            const float2 nm = norm[4 * kc + j];
-            x = (src[j] - nm.x) * nm.y;
-          }
+          const float x = 4 * kc + j < D ? (src[j] - nm[j].x) * nm[j].y : 0.0f;
           hi[j] = tf32_rna(x);
           lo[j] = x - __uint_as_float(hi[j]);
         }
@@ -419,22 +485,54 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
       }
     }
   };
-  auto issue_layer1 = [&]() {                              // thread 0 only
+  // descriptors advance by two K chunks per MMA (K = 8 tf32): the 14-bit address field never carries
+  auto issue_layer1 = [&]() {                              // warp 0, all lanes (warp-uniform)
     constexpr uint32_t idesc = make_idesc(kN1);
-    const uint32_t lbo_b = kN1 * 16;
+    constexpr uint32_t lbo_b = kN1 * 16;
     mma_ss(tbase + R0, ones_desc, make_desc(bb1_s, lbo_b, kSbo), idesc, 0);
     if (X3) mma_ss(tbase + R0, ones_desc, make_desc(bb1_s + lo_off, lbo_b, kSbo), idesc, 1);
+    uint64_t ah = make_desc(a1hi_s, kLboA, kSbo), al = make_desc(a1lo_s, kLboA, kSbo);
+    uint64_t bh = make_desc(b1_s, lbo_b, kSbo), bl = make_desc(b1_s + lo_off, lbo_b, kSbo);
     for (int ks = 0; ks < K1 / 8; ++ks) {
-      const uint64_t ah = make_desc(a1hi_s + ks * 2 * kLboA, kLboA, kSbo), bh = make_desc(b1_s + ks * 2 * lbo_b, lbo_b, kSbo);
       if (X3) {
-        const uint64_t al = make_desc(a1lo_s + ks * 2 * kLboA, kLboA, kSbo);
-        const uint64_t bl = make_desc(b1_s + lo_off + ks * 2 * lbo_b, lbo_b, kSbo);
         mma_ss(tbase + R0, al, bh, idesc, 1);
         mma_ss(tbase + R0, ah, bl, idesc, 1);
       }
       mma_ss(tbase + R0, ah, bh, idesc, 1);
+      ah += (2 * kLboA) >> 4; al += (2 * kLboA) >> 4; bh += (2 * lbo_b) >> 4; bl += (2 * lbo_b) >> 4;
     }
     tc_commit(bar1);
+  };
+  auto issue_layer2 = [&]() {                              // warp 0, all lanes (warp-uniform)
+    constexpr uint32_t idesc = make_idesc(64);
+    constexpr uint32_t lbo_b = 64 * 16;
+    constexpr uint64_t kstep = (2 * lbo_b) >> 4;
+    const uint64_t bh_a = make_desc(b2a_s, lbo_b, kSbo), bh_c = make_desc(b2c_s, lbo_b, kSbo);
+    const uint64_t bl_a = make_desc(b2a_s + lo_off, lbo_b, kSbo), bl_c = make_desc(b2c_s + lo_off, lbo_b, kSbo);
+    // bias into the first accumulator of each net
+    mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s, lbo_b, kSbo), idesc, 0);
+    mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s, lbo_b, kSbo), idesc, 0);
+    if (X3) {
+      mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s + lo_off, lbo_b, kSbo), idesc, 1);
+      mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s + lo_off, lbo_b, kSbo), idesc, 1);
+    }
+    // rolled over the k-steps (code size: the whole tile loop should stay resident in the instruction cache);
+    // within a step the two nets' (independent) accumulators alternate
+    uint32_t a_hi = tbase + R0, a_lo = tbase + R2;
+    uint64_t bha = bh_a, bhc = bh_c, bla = bl_a, blc = bl_c;
+#pragma unroll 1
+    for (int ks = 0; ks < 8; ++ks) {
+      if (X3) {
+        mma_ts(tbase + R1, a_lo, bha, idesc, 1);
+        mma_ts(tbase + R1 + 64, a_lo + 64, bhc, idesc, 1);
+        mma_ts(tbase + R1, a_hi, bla, idesc, 1);
+        mma_ts(tbase + R1 + 64, a_hi + 64, blc, idesc, 1);
+      }
+      mma_ts(tbase + R1, a_hi, bha, idesc, 1);
+      mma_ts(tbase + R1 + 64, a_hi + 64, bhc, idesc, 1);
+      a_hi += 8; a_lo += 8; bha += kstep; bhc += kstep; bla += kstep; blc += kstep;
+    }
+    tc_commit(bar2);
   };
 
   // ---- prologue: first tile
@@ -446,85 +544,88 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
   fence_async_smem();                // generic-proxy writes of X / ones -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (tile + gridDim.x < a.n_tiles) stage_fetch(tile + gridDim.x);          // `stage` was consumed before the barrier
+  if (warp == 0) {
     tc_fence_after();
     issue_layer1();
   }
-  if (tile + gridDim.x < a.n_tiles) stage_fetch(tile + gridDim.x);          // `stage` was consumed before the barrier
+  const float* w3a = common;
+  const float* w3c = common + 256;
+  const float* b3 = common + 320;
 
   uint32_t par = 0;
-  for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1) {
+  [[maybe_unused]] int tcount = 0;
+  for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1, ++tcount) {
     const int64_t env0 = tile * kTile;
     const int64_t next = tile + gridDim.x;
     const bool has_next = next < a.n_tiles;
     // ---- layer 1 done -> activation in place
+    TC_STAMP(0);
     mbar_wait(bar1, par);
     tc_fence_after();
-    hidden_epilogue<X3>(taddr, R0, cg);
+    TC_STAMP(1);
+    hidden_epilogue<X3>(taddr, cg);
     tmem_wait_st();
+    TC_STAMP(2);
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    TC_STAMP(3);
+    if (warp == 0) {
       tc_fence_after();
-      constexpr uint32_t idesc = make_idesc(64);
-      const uint32_t lbo_b = 64 * 16;
-      for (int net = 0; net < 2; ++net) {
-        const uint32_t bs = net ? b2c_s : b2a_s, bbs = net ? bb2c_s : bb2a_s;
-        const uint32_t d = tbase + R1 + 64 * net, ahi = tbase + R0 + 64 * net, alo = tbase + R2 + 64 * net;
-        mma_ss(d, ones_desc, make_desc(bbs, lbo_b, kSbo), idesc, 0);
-        if (X3) mma_ss(d, ones_desc, make_desc(bbs + lo_off, lbo_b, kSbo), idesc, 1);
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t bh = make_desc(bs + ks * 2 * lbo_b, lbo_b, kSbo);
-          if (X3) {
-            mma_ts(d, alo + ks * 8, bh, idesc, 1);
-            mma_ts(d, ahi + ks * 8, make_desc(bs + lo_off + ks * 2 * lbo_b, lbo_b, kSbo), idesc, 1);
-          }
-          mma_ts(d, ahi + ks * 8, bh, idesc, 1);
-        }
-      }
-      tc_commit(bar2);
+#ifdef PDX_TC_TIMING
+      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 10] = clock64();
+#endif
+      issue_layer2();
+#ifdef PDX_TC_TIMING
+      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 11] = clock64();
+      if (tid == 0) mbar_wait_thread(bar2, par);
+      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 12] = clock64();
+      __syncwarp();
+#endif
     }
     // ---- while layer 2 runs: the next tile's observations (already in `stage`) -> X (layer 1 of this
     // tile has completed, so the X buffer is free)
     if (has_next) {
       mbar_wait(bar_x, par ^ 1);
+      TC_STAMP(4);
       stage_to_x();
     }
-    // ---- layer 2 done -> activation in place
+    TC_STAMP(5);
+    // ---- layer 2 done -> activation, layer 3 partial dot products
     mbar_wait(bar2, par);
     tc_fence_after();
-    hidden_epilogue<X3>(taddr, R1, cg);
-    tmem_wait_st();
+    TC_STAMP(6);
+    float part[5];
+    output_epilogue<X3>(taddr, cg, w3a, w3c, part);
+    {
+      float4* dst = reinterpret_cast<float4*>(part_sm + (cg * kTile + row) * 8);
+      dst[0] = make_float4(part[0], part[1], part[2], part[3]);
+      dst[1] = make_float4(part[4], 0.f, 0.f, 0.f);
+    }
+    TC_STAMP(7);
     fence_async_smem();               // X of the next tile -> async proxy
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    // `stage` is free again, layer 2 has completed (a2 is dead): fetch tile + 2, start layer 1 of tile + 1
+    if (next + gridDim.x < a.n_tiles) stage_fetch(next + gridDim.x);
+    if (warp == 0 && has_next) {
       tc_fence_after();
-      constexpr uint32_t idesc = make_idesc(kN3);
-      const uint32_t lbo_b = kN3 * 16;
-      mma_ss(tbase + D3, ones_desc, make_desc(bb3_s, lbo_b, kSbo), idesc, 0);
-      if (X3) mma_ss(tbase + D3, ones_desc, make_desc(bb3_s + lo_off, lbo_b, kSbo), idesc, 1);
-      for (int ks = 0; ks < 16; ++ks) {
-        const uint64_t bh = make_desc(b3_s + ks * 2 * lbo_b, lbo_b, kSbo);
-        if (X3) {
-          mma_ts(tbase + D3, tbase + R2 + ks * 8, bh, idesc, 1);
-          mma_ts(tbase + D3, tbase + R1 + ks * 8, make_desc(b3_s + lo_off + ks * 2 * lbo_b, lbo_b, kSbo), idesc, 1);
-        }
-        mma_ts(tbase + D3, tbase + R1 + ks * 8, bh, idesc, 1);
-      }
-      tc_commit(bar3);
-      if (X3 && has_next) issue_layer1();                 // D3 has its own columns: start the next tile now
+      issue_layer1();
     }
-    if (next + gridDim.x < a.n_tiles) stage_fetch(next + gridDim.x);        // `stage` is free again
-    // ---- output layer: mu (columns 0..3), v (column 4); sample, log-probability, stores
-    mbar_wait(bar3, par);
-    tc_fence_after();
+    TC_STAMP(8);
+    // ---- output: mu, v = bias + partial sums; sample, log-probability, stores
     if (cg == 0) {
-      uint32_t r[16];
-      tmem_ld16(taddr + D3, r);
-      tmem_wait_ld();
       const int64_t i = env0 + row;
       if (i < a.n) {
+        float mu[4] = {b3[0], b3[1], b3[2], b3[3]};
+        float v = b3[4];
+#pragma unroll
+        for (int g = 0; g < Cfg::kNcg; ++g) {
+          const float4* src = reinterpret_cast<const float4*>(part_sm + (g * kTile + row) * 8);
+          const float4 p0 = src[0];
+          mu[0] += p0.x; mu[1] += p0.y; mu[2] += p0.z; mu[3] += p0.w;
+          v += src[1].x;
+        }
         // same Philox counters as k_policy: identical draws for the same (seed, counter, env)
         const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
@@ -532,29 +633,21 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
         pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
         pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
         float lp = 0.0f;
-        float av[4] = {0.f, 0.f, 0.f, 0.f}, mu[4];
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          mu[k] = __uint_as_float(r[k]);
           if (k < a.act_dim) {
             av[k] = fmaf(act_std[k], eps[k], mu[k]);
             lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
           }
         }
         reinterpret_cast<float4*>(a.act)[i] = make_float4(av[0], av[1], av[2], av[3]);
-        a.val[i] = __uint_as_float(r[4]);
+        a.val[i] = v;
         a.logp[i] = lp;
         if (a.mu) reinterpret_cast<float4*>(a.mu)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
       }
     }
-    if (!X3 && has_next) {            // D3 shares columns with D1: wait for the readers, then layer 1 of the next tile
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_layer1();
-      }
-    }
+    TC_STAMP(9);
   }
   tc_fence_before();
   __syncthreads();
@@ -562,8 +655,9 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
 }
 
 size_t tc_smem_bytes(int k1, int obs_dim, bool x3) {
-  const size_t nb = x3 ? 2 : 1;
-  return 80 + (size_t)k1 * 8 + kOnesBytes + nb * tc_b_words(k1) * 4 + nb * (k1 / 4) * kLboA + (size_t)kTile * obs_dim * 4;
+  const size_t nb = x3 ? 2 : 1, ncg = x3 ? 4 : 2;
+  return 80 + (size_t)k1 * 8 + kOnesBytes + ncg * kTile * 8 * 4 + (kCommonWords + nb * tc_b_words(k1)) * 4 +
+         nb * (k1 / 4) * kLboA + (size_t)kTile * obs_dim * 4;
 }
 
 int tc_select_device_of(const void* ptr) {
@@ -588,10 +682,16 @@ bool tc_shapes_ok(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t pr
 
 }  // namespace
 
+#ifdef PDX_TC_TIMING
+extern "C" int pdx_policy_tc_timing(long long* out) {
+  return cudaMemcpyFromSymbol(out, tc_timing, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 extern "C" int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
   if (!tc_shapes_ok(obs_dim, pi, v, precision)) return PDX_ERR_INVALID;
   const int k1 = (obs_dim + 7) & ~7;
-  return (precision == 3 ? 2 : 1) * tc_b_words(k1);
+  return kCommonWords + (precision == 3 ? 2 : 1) * tc_b_words(k1);
 }
 
 extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream) {
