@@ -93,6 +93,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait_thread(bar, parity);
   __syncwarp();
 }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -281,7 +283,7 @@ struct TcCfg {
   static constexpr int kMinBlocks = X3 ? 1 : 2;
   static constexpr int kSplit = 1;                     // layer-2 accumulators per net (2 = K halves summed in the epilogue: no gain measured)
   // TMEM column regions: R0 = D1 -> a2 (hi), R1 = D2 (first K half), R2 = a2 lo, R3 = D2 (second K half)
-  static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256, kR3 = 384;
+  static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256, kR3 = 384;     // kR3 only with kSplit = 2
 };
 
 // tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA; saturates correctly
@@ -369,14 +371,16 @@ __device__ __forceinline__ void output_epilogue(uint32_t taddr, int cg, const fl
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_policy_tc(const TcArgs a) {
+__global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlocks) k_policy_tc(const TcArgs a) {
   using Cfg = TcCfg<X3>;
-  constexpr int NT = Cfg::kThreads;
+  constexpr int NT = Cfg::kThreads;                                        // epilogue threads; warp NT/32 is the issuer
   constexpr int NB = X3 ? 2 : 1;                                           // operand images: hi (+ lo)
-  constexpr uint32_t R0 = Cfg::kR0, R1 = Cfg::kR1, R2 = Cfg::kR2, R3 = Cfg::kR3;
+  constexpr uint32_t R0 = Cfg::kR0, R1 = Cfg::kR1, R2 = Cfg::kR2;
+  constexpr int kBarEpi = 1, kBarA2 = 2, kBarX = 3;                        // named barriers (0 = __syncthreads)
   extern __shared__ __align__(128) uint8_t tc_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = a.obs_dim, K1 = a.k1;
+  const bool issuer = warp == NT / 32;
 
   // ---- shared-memory plan
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tc_smem);                   // [0] weights [1..2] layers [3] obs tile
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
   float* stage = reinterpret_cast<float*>(a1hi + NB * (K1 / 4) * kLboA);   // raw observation tile [128][D]
   const uint32_t bar_w = smem_u32(mbar), bar1 = bar_w + 8, bar2 = bar_w + 16, bar_x = bar_w + 24;
 
-  // ---- one-time setup
+  // ---- one-time setup (all warps)
   if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   if (tid == 32) {
     mbar_init(bar_w, 1); mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar_x, 1);
@@ -404,250 +408,246 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads, TcCfg<X3>::kMinBlocks) k_
     act_std[tid] = expf(ls);
     act_std[4 + tid] = ls;
   }
-  for (int k = tid; k < K1; k += NT) {
+  for (int k = tid; k < K1; k += NT + 32) {
     float m = 0.0f, inv = 1.0f;
     if (k < D && a.std) { m = a.mean[k]; inv = 1.0f / (a.std[k] + a.eps); }
     norm[k] = make_float2(m, inv);
   }
-  for (int e = tid; e < (int)kOnesBytes / 4; e += NT)                       // ones[m][k]: k = 0 -> 1
+  for (int e = tid; e < (int)kOnesBytes / 4; e += NT + 32)                  // ones[m][k]: k = 0 -> 1
     reinterpret_cast<float*>(ones)[e] = (e < 512 && (e & 3) == 0) ? 1.0f : 0.0f;
   const int n_chunks = (D + 3) >> 2;                                        // 16-byte K chunks that hold data
-  for (int e = tid; e < kTile * (K1 / 4 - n_chunks); e += NT) {             // K padding chunks: zero, once
+  for (int e = tid; e < kTile * (K1 / 4 - n_chunks); e += NT + 32) {        // K padding chunks: zero, once
     const int m = e & (kTile - 1), kc = n_chunks + (e >> 7);
     *reinterpret_cast<float4*>(a1hi + kc * kLboA + m * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (X3) *reinterpret_cast<float4*>(a1lo + kc * kLboA + m * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  fence_async_smem();                // ones / padding (generic proxy) -> visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  if (tid == 0) {                                          // weight image: one bulk copy (TMA engine)
-    const uint32_t bytes = (uint32_t)((kCommonWords + NB * bwords) * 4);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(common)),
-                 "l"(a.packed), "r"(bytes), "r"(bar_w)
-                 : "memory");
-  }
-
-  const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4;
-  const uint32_t bb1_s = b2c_s + kB2Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4;
-  const uint32_t lo_off = (uint32_t)bwords * 4;            // Blo = Bhi + lo_off (bytes)
-  const uint32_t a1hi_s = smem_u32(a1hi), a1lo_s = smem_u32(a1lo);
-  const uint64_t ones_desc = make_desc(smem_u32(ones), 2048, kSbo);
-
-  const int q = warp & 3, cg = warp >> 2;                  // TMEM lane quarter, column group
-  const uint32_t taddr = tbase + ((uint32_t)(32 * q) << 16);
-  const int row = 32 * q + lane;                           // this thread's environment within the tile
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0;
+  // a tile travels by ONE bulk copy (TMA engine) when it is complete and 16-byte aligned; the last,
+  // partial tile is copied by the epilogue threads themselves
+  auto tile_is_bulk = [&](int64_t tile) { return (a.n - tile * kTile) >= kTile && obs_aligned; };
 
-  // raw observation tile -> `stage`: one bulk copy when the tile is full and 16-byte aligned (thread 0),
-  // otherwise (last partial tile) a cooperative copy with zero fill.  Completion is signalled on bar_x.
-  auto stage_fetch = [&](int64_t tile) {
-    const int64_t env0 = tile * kTile;
-    const bool full = (a.n - env0) >= kTile && obs_aligned;
-    if (full) {
-      if (tid == 0) {
+  if (issuer) {
+    // =====================================================================================
+    //  issuer warp: TMA copies and every tcgen05.mma.  All 32 lanes run this code with
+    //  warp-uniform values; the wrappers elect the lane that executes the instruction.
+    // =====================================================================================
+    const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4;
+    const uint32_t bb1_s = b2c_s + kB2Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4;
+    const uint32_t lo_off = (uint32_t)bwords * 4;          // Blo = Bhi + lo_off (bytes)
+    const uint32_t a1hi_s = smem_u32(a1hi), a1lo_s = smem_u32(a1lo);
+    const uint64_t ones_desc = make_desc(smem_u32(ones), 2048, kSbo);
+    auto fetch = [&](int64_t tile) {
+      if (tile < a.n_tiles && tile_is_bulk(tile) && lane == 0) {
         const uint32_t bytes = (uint32_t)(kTile * D * 4);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_x), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)),
-                     "l"(a.obs + env0 * D), "r"(bytes), "r"(bar_x)
+                     "l"(a.obs + tile * kTile * D), "r"(bytes), "r"(bar_x)
                      : "memory");
       }
-    } else {
-      const int n_elem = (int)(((a.n - env0) < kTile ? (a.n - env0) : kTile) * D);
-      const float* src = a.obs + env0 * D;
-      for (int e = tid; e < kTile * D; e += NT) stage[e] = e < n_elem ? __ldg(src + e) : 0.0f;
-      __syncthreads();                                     // every caller reaches this point together
-      if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_x) : "memory");
-    }
-  };
-  // `stage` -> X: standardise, split, store in the canonical K-major layout.  Sixteen lanes walk the
-  // 16-byte K chunks of one environment row (contiguous shared-memory reads), two rows per warp.
-  auto stage_to_x = [&]() {
-    const int kc = tid & 15;
-    if (kc < n_chunks) {
-      float2 nm[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) nm[j] = 4 * kc + j < D ? norm[4 * kc + j] : make_float2(0.0f, 0.0f);
-#pragma unroll 4
-      for (int m = tid >> 4; m < kTile; m += NT / 16) {
-        const float* src = stage + m * D + 4 * kc;
-        uint32_t hi[4];
-        float lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x = 4 * kc + j < D ? (src[j] - nm[j].x) * nm[j].y : 0.0f;
-          hi[j] = tf32_rna(x);
-          lo[j] = x - __uint_as_float(hi[j]);
-        }
-        *reinterpret_cast<uint4*>(a1hi + kc * kLboA + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (X3) *reinterpret_cast<float4*>(a1lo + kc * kLboA + m * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
-    }
-  };
-  // descriptors advance by two K chunks per MMA (K = 8 tf32): the 14-bit address field never carries
-  auto issue_layer1 = [&]() {                              // warp 0, all lanes (warp-uniform)
-    constexpr uint32_t idesc = make_idesc(kN1);
-    constexpr uint32_t lbo_b = kN1 * 16;
-    mma_ss(tbase + R0, ones_desc, make_desc(bb1_s, lbo_b, kSbo), idesc, 0);
-    if (X3) mma_ss(tbase + R0, ones_desc, make_desc(bb1_s + lo_off, lbo_b, kSbo), idesc, 1);
-    uint64_t ah = make_desc(a1hi_s, kLboA, kSbo), al = make_desc(a1lo_s, kLboA, kSbo);
-    uint64_t bh = make_desc(b1_s, lbo_b, kSbo), bl = make_desc(b1_s + lo_off, lbo_b, kSbo);
-    for (int ks = 0; ks < K1 / 8; ++ks) {
-      if (X3) {
-        mma_ss(tbase + R0, al, bh, idesc, 1);
-        mma_ss(tbase + R0, ah, bl, idesc, 1);
-      }
-      mma_ss(tbase + R0, ah, bh, idesc, 1);
-      ah += (2 * kLboA) >> 4; al += (2 * kLboA) >> 4; bh += (2 * lbo_b) >> 4; bl += (2 * lbo_b) >> 4;
-    }
-    tc_commit(bar1);
-  };
-  auto issue_layer2 = [&]() {                              // warp 0, all lanes (warp-uniform)
-    constexpr uint32_t idesc = make_idesc(64);
-    constexpr uint32_t lbo_b = 64 * 16;
-    constexpr uint64_t kstep = (2 * lbo_b) >> 4;
-    const uint64_t bh_a = make_desc(b2a_s, lbo_b, kSbo), bh_c = make_desc(b2c_s, lbo_b, kSbo);
-    const uint64_t bl_a = make_desc(b2a_s + lo_off, lbo_b, kSbo), bl_c = make_desc(b2c_s + lo_off, lbo_b, kSbo);
-    // bias into the first accumulator of each net
-    mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s, lbo_b, kSbo), idesc, 0);
-    mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s, lbo_b, kSbo), idesc, 0);
-    if (X3) {
-      mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s + lo_off, lbo_b, kSbo), idesc, 1);
-      mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s + lo_off, lbo_b, kSbo), idesc, 1);
-    }
-    // rolled over the k-steps (code size: the whole tile loop should stay resident in the instruction cache);
-    // within a step the two nets' (independent) accumulators alternate
-    uint32_t a_hi = tbase + R0, a_lo = tbase + R2;
-    uint64_t bha = bh_a, bhc = bh_c, bla = bl_a, blc = bl_c;
+      __syncwarp();
+    };
+    // descriptors advance by two K chunks per MMA (K = 8 tf32): the 14-bit address field never carries
+    auto issue_layer1 = [&]() {
+      constexpr uint32_t idesc = make_idesc(kN1);
+      constexpr uint32_t lbo_b = kN1 * 16;
+      mma_ss(tbase + R0, ones_desc, make_desc(bb1_s, lbo_b, kSbo), idesc, 0);
+      if (X3) mma_ss(tbase + R0, ones_desc, make_desc(bb1_s + lo_off, lbo_b, kSbo), idesc, 1);
+      uint64_t ah = make_desc(a1hi_s, kLboA, kSbo), al = make_desc(a1lo_s, kLboA, kSbo);
+      uint64_t bh = make_desc(b1_s, lbo_b, kSbo), bl = make_desc(b1_s + lo_off, lbo_b, kSbo);
 #pragma unroll 1
-    for (int ks = 0; ks < 8; ++ks) {
-      if (X3) {
-        mma_ts(tbase + R1, a_lo, bha, idesc, 1);
-        mma_ts(tbase + R1 + 64, a_lo + 64, bhc, idesc, 1);
-        mma_ts(tbase + R1, a_hi, bla, idesc, 1);
-        mma_ts(tbase + R1 + 64, a_hi + 64, blc, idesc, 1);
+      for (int ks = 0; ks < K1 / 8; ++ks) {
+        if (X3) {
+          mma_ss(tbase + R0, al, bh, idesc, 1);
+          mma_ss(tbase + R0, ah, bl, idesc, 1);
+        }
+        mma_ss(tbase + R0, ah, bh, idesc, 1);
+        ah += (2 * kLboA) >> 4; al += (2 * kLboA) >> 4; bh += (2 * lbo_b) >> 4; bl += (2 * lbo_b) >> 4;
       }
-      mma_ts(tbase + R1, a_hi, bha, idesc, 1);
-      mma_ts(tbase + R1 + 64, a_hi + 64, bhc, idesc, 1);
-      a_hi += 8; a_lo += 8; bha += kstep; bhc += kstep; bla += kstep; blc += kstep;
-    }
-    tc_commit(bar2);
-  };
+      tc_commit(bar1);
+    };
+    auto issue_layer2 = [&]() {
+      constexpr uint32_t idesc = make_idesc(64);
+      constexpr uint32_t lbo_b = 64 * 16;
+      constexpr uint64_t kstep = (2 * lbo_b) >> 4;
+      uint64_t bha = make_desc(b2a_s, lbo_b, kSbo), bhc = make_desc(b2c_s, lbo_b, kSbo);
+      uint64_t bla = make_desc(b2a_s + lo_off, lbo_b, kSbo), blc = make_desc(b2c_s + lo_off, lbo_b, kSbo);
+      mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s, lbo_b, kSbo), idesc, 0);
+      mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s, lbo_b, kSbo), idesc, 0);
+      if (X3) {
+        mma_ss(tbase + R1, ones_desc, make_desc(bb2a_s + lo_off, lbo_b, kSbo), idesc, 1);
+        mma_ss(tbase + R1 + 64, ones_desc, make_desc(bb2c_s + lo_off, lbo_b, kSbo), idesc, 1);
+      }
+      // rolled over the k-steps; within a step the two nets' (independent) accumulators alternate
+      uint32_t a_hi = tbase + R0, a_lo = tbase + R2;
+#pragma unroll 1
+      for (int ks = 0; ks < 8; ++ks) {
+        if (X3) {
+          mma_ts(tbase + R1, a_lo, bha, idesc, 1);
+          mma_ts(tbase + R1 + 64, a_lo + 64, bhc, idesc, 1);
+          mma_ts(tbase + R1, a_hi, bla, idesc, 1);
+          mma_ts(tbase + R1 + 64, a_hi + 64, blc, idesc, 1);
+        }
+        mma_ts(tbase + R1, a_hi, bha, idesc, 1);
+        mma_ts(tbase + R1 + 64, a_hi + 64, bhc, idesc, 1);
+        a_hi += 8; a_lo += 8; bha += kstep; bhc += kstep; bla += kstep; blc += kstep;
+      }
+      tc_commit(bar2);
+    };
 
-  // ---- prologue: first tile
-  int64_t tile = blockIdx.x;
-  stage_fetch(tile);
-  mbar_wait(bar_x, 0);
-  stage_to_x();
-  mbar_wait(bar_w, 0);               // weight image landed (async-proxy writes, visible after the wait)
-  fence_async_smem();                // generic-proxy writes of X / ones -> visible to the tensor core (async proxy)
-  tc_fence_before();
-  __syncthreads();
-  if (tile + gridDim.x < a.n_tiles) stage_fetch(tile + gridDim.x);          // `stage` was consumed before the barrier
-  if (warp == 0) {
+    int64_t tile = blockIdx.x;
+    if (lane == 0) {                                       // weight image: one bulk copy
+      const uint32_t bytes = (uint32_t)((kCommonWords + NB * bwords) * 4);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(common)),
+                   "l"(a.packed), "r"(bytes), "r"(bar_w)
+                   : "memory");
+    }
+    __syncwarp();
+    fetch(tile);
+    named_bar_sync(kBarX, NT + 32);                        // X(tile 0) built, `stage` consumed
+    fetch(tile + gridDim.x);
+    mbar_wait(bar_w, 0);
     tc_fence_after();
     issue_layer1();
-  }
-  const float* w3a = common;
-  const float* w3c = common + 256;
-  const float* b3 = common + 320;
-
-  uint32_t par = 0;
-  [[maybe_unused]] int tcount = 0;
-  for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1, ++tcount) {
-    const int64_t env0 = tile * kTile;
-    const int64_t next = tile + gridDim.x;
-    const bool has_next = next < a.n_tiles;
-    // ---- layer 1 done -> activation in place
-    TC_STAMP(0);
-    mbar_wait(bar1, par);
-    tc_fence_after();
-    TC_STAMP(1);
-    hidden_epilogue<X3>(taddr, cg);
-    tmem_wait_st();
-    TC_STAMP(2);
-    tc_fence_before();
-    __syncthreads();
-    TC_STAMP(3);
-    if (warp == 0) {
+    uint32_t par = 0;
+    for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1) {
+      const int64_t next = tile + gridDim.x;
+      named_bar_sync(kBarA2, NT + 32);                     // a2 of this tile is in TMEM
       tc_fence_after();
-#ifdef PDX_TC_TIMING
-      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 10] = clock64();
-#endif
       issue_layer2();
-#ifdef PDX_TC_TIMING
-      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 11] = clock64();
-      if (tid == 0) mbar_wait_thread(bar2, par);
-      if (blockIdx.x == 0 && tid == 0 && tcount < 8) tc_timing[tcount * 16 + 12] = clock64();
-      __syncwarp();
-#endif
-    }
-    // ---- while layer 2 runs: the next tile's observations (already in `stage`) -> X (layer 1 of this
-    // tile has completed, so the X buffer is free)
-    if (has_next) {
-      mbar_wait(bar_x, par ^ 1);
-      TC_STAMP(4);
-      stage_to_x();
-    }
-    TC_STAMP(5);
-    // ---- layer 2 done -> activation, layer 3 partial dot products
-    mbar_wait(bar2, par);
-    tc_fence_after();
-    TC_STAMP(6);
-    float part[5];
-    output_epilogue<X3>(taddr, cg, w3a, w3c, part);
-    {
-      float4* dst = reinterpret_cast<float4*>(part_sm + (cg * kTile + row) * 8);
-      dst[0] = make_float4(part[0], part[1], part[2], part[3]);
-      dst[1] = make_float4(part[4], 0.f, 0.f, 0.f);
-    }
-    TC_STAMP(7);
-    fence_async_smem();               // X of the next tile -> async proxy
-    tc_fence_before();
-    __syncthreads();
-    // `stage` is free again, layer 2 has completed (a2 is dead): fetch tile + 2, start layer 1 of tile + 1
-    if (next + gridDim.x < a.n_tiles) stage_fetch(next + gridDim.x);
-    if (warp == 0 && has_next) {
-      tc_fence_after();
-      issue_layer1();
-    }
-    TC_STAMP(8);
-    // ---- output: mu, v = bias + partial sums; sample, log-probability, stores
-    if (cg == 0) {
-      const int64_t i = env0 + row;
-      if (i < a.n) {
-        float mu[4] = {b3[0], b3[1], b3[2], b3[3]};
-        float v = b3[4];
-#pragma unroll
-        for (int g = 0; g < Cfg::kNcg; ++g) {
-          const float4* src = reinterpret_cast<const float4*>(part_sm + (g * kTile + row) * 8);
-          const float4 p0 = src[0];
-          mu[0] += p0.x; mu[1] += p0.y; mu[2] += p0.z; mu[3] += p0.w;
-          v += src[1].x;
-        }
-        // same Philox counters as k_policy: identical draws for the same (seed, counter, env)
-        const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
-                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-        float eps[4];
-        pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
-        pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
-        float lp = 0.0f;
-        float av[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < a.act_dim) {
-            av[k] = fmaf(act_std[k], eps[k], mu[k]);
-            lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
-          }
-        }
-        reinterpret_cast<float4*>(a.act)[i] = make_float4(av[0], av[1], av[2], av[3]);
-        a.val[i] = v;
-        a.logp[i] = lp;
-        if (a.mu) reinterpret_cast<float4*>(a.mu)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+      if (next < a.n_tiles) {
+        named_bar_sync(kBarX, NT + 32);                    // X(next) built, `stage` consumed
+        fetch(next + gridDim.x);
+        mbar_wait(bar2, par);                              // layer 2 has read a2: its columns are free for D1(next)
+        tc_fence_after();
+        issue_layer1();
       }
     }
-    TC_STAMP(9);
+  } else {
+    // =====================================================================================
+    //  epilogue warps: element-wise work, one thread = one environment row of the tile
+    // =====================================================================================
+    const int q = warp & 3, cg = warp >> 2;                // TMEM lane quarter, column group
+    const uint32_t taddr = tbase + ((uint32_t)(32 * q) << 16);
+    const int row = 32 * q + lane;                         // this thread's environment within the tile
+    const float* w3a = common;
+    const float* w3c = common + 256;
+    const float* b3 = common + 320;
+    // raw tile in `stage` (bulk copy signalled on bar_x, or copied here) -> X: standardise, split, store in
+    // the canonical K-major layout.  Sixteen lanes walk the 16-byte K chunks of one environment row
+    // (contiguous shared-memory reads), two rows per warp.
+    auto build_x = [&](int64_t tile, uint32_t parity) {
+      if (tile_is_bulk(tile)) {
+        mbar_wait(bar_x, parity);
+      } else {
+        const int64_t env0 = tile * kTile;
+        const int n_elem = (int)(((a.n - env0) < kTile ? (a.n - env0) : kTile) * D);
+        const float* src = a.obs + env0 * D;
+        for (int e = tid; e < kTile * D; e += NT) stage[e] = e < n_elem ? __ldg(src + e) : 0.0f;
+        named_bar_sync(kBarEpi, NT);
+      }
+      const int kc = tid & 15;
+      if (kc < n_chunks) {
+        float2 nm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nm[j] = 4 * kc + j < D ? norm[4 * kc + j] : make_float2(0.0f, 0.0f);
+#pragma unroll 4
+        for (int m = tid >> 4; m < kTile; m += NT / 16) {
+          const float* src = stage + m * D + 4 * kc;
+          uint32_t hi[4];
+          float lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = 4 * kc + j < D ? (src[j] - nm[j].x) * nm[j].y : 0.0f;
+            hi[j] = tf32_rna(x);
+            lo[j] = x - __uint_as_float(hi[j]);
+          }
+          *reinterpret_cast<uint4*>(a1hi + kc * kLboA + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (X3) *reinterpret_cast<float4*>(a1lo + kc * kLboA + m * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_async_smem();            // generic-proxy writes of X -> visible to the tensor core (async proxy)
+      named_bar_arrive(kBarX, NT + 32);
+    };
+
+    int64_t tile = blockIdx.x;
+    build_x(tile, 0);
+    mbar_wait(bar_w, 0);             // layer-3 weights / biases are read from the image below
+    uint32_t par = 0;
+    [[maybe_unused]] int tcount = 0;
+    for (; tile < a.n_tiles; tile += gridDim.x, par ^= 1, ++tcount) {
+      const int64_t env0 = tile * kTile;
+      const int64_t next = tile + gridDim.x;
+      // ---- layer 1 done -> activation in place (TMEM), hand a2 to the issuer
+      TC_STAMP(0);
+      mbar_wait(bar1, par);
+      tc_fence_after();
+      TC_STAMP(1);
+      hidden_epilogue<X3>(taddr, cg);
+      tmem_wait_st();
+      tc_fence_before();
+      named_bar_arrive(kBarA2, NT + 32);
+      TC_STAMP(2);
+      // ---- while layer 2 runs: the next tile's observations -> X (layer 1 of this tile has completed,
+      // so the X buffer is free)
+      if (next < a.n_tiles) build_x(next, par ^ 1);
+      TC_STAMP(3);
+      // ---- layer 2 done -> activation, layer 3 partial dot products
+      mbar_wait(bar2, par);
+      tc_fence_after();
+      TC_STAMP(4);
+      float part[5];
+      output_epilogue<X3>(taddr, cg, w3a, w3c, part);
+      {
+        float4* dst = reinterpret_cast<float4*>(part_sm + (cg * kTile + row) * 8);
+        dst[0] = make_float4(part[0], part[1], part[2], part[3]);
+        dst[1] = make_float4(part[4], 0.f, 0.f, 0.f);
+      }
+      tc_fence_before();
+      TC_STAMP(5);
+      named_bar_sync(kBarEpi, NT);
+      TC_STAMP(6);
+      // ---- output: mu, v = bias + partial sums; sample, log-probability, stores
+      if (cg == 0) {
+        const int64_t i = env0 + row;
+        if (i < a.n) {
+          float mu[4] = {b3[0], b3[1], b3[2], b3[3]};
+          float v = b3[4];
+#pragma unroll
+          for (int g = 0; g < Cfg::kNcg; ++g) {
+            const float4* src = reinterpret_cast<const float4*>(part_sm + (g * kTile + row) * 8);
+            const float4 p0 = src[0];
+            mu[0] += p0.x; mu[1] += p0.y; mu[2] += p0.z; mu[3] += p0.w;
+            v += src[1].x;
+          }
+          // same Philox counters as k_policy: identical draws for the same (seed, counter, env)
+          const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+                                     make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+          float eps[4];
+          pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
+          pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
+          float lp = 0.0f;
+          float av[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < a.act_dim) {
+              av[k] = fmaf(act_std[k], eps[k], mu[k]);
+              lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
+            }
+          }
+          reinterpret_cast<float4*>(a.act)[i] = make_float4(av[0], av[1], av[2], av[3]);
+          a.val[i] = v;
+          a.logp[i] = lp;
+          if (a.mu) reinterpret_cast<float4*>(a.mu)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+        }
+      }
+      TC_STAMP(7);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -736,7 +736,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   // persistent CTAs: TMEM (512 columns per SM) admits one precision-3 CTA or two precision-1 CTAs per SM
   const int64_t resident = (int64_t)sms * (x3 ? 1 : ((size_t)2 * smem <= (size_t)227 * 1024 ? 2 : 1));
   const unsigned grid = (unsigned)(a.n_tiles < resident ? a.n_tiles : resident);
-  if (x3) k_policy_tc<true><<<grid, TcCfg<true>::kThreads, smem, (cudaStream_t)stream>>>(a);
-  else k_policy_tc<false><<<grid, TcCfg<false>::kThreads, smem, (cudaStream_t)stream>>>(a);
+  if (x3) k_policy_tc<true><<<grid, TcCfg<true>::kThreads + 32, smem, (cudaStream_t)stream>>>(a);
+  else k_policy_tc<false><<<grid, TcCfg<false>::kThreads + 32, smem, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
 }

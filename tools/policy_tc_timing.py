@@ -20,9 +20,8 @@ torch.cuda.synchronize()
 buf = (C.c_longlong * 128)()
 L = lib.load()
 assert L.pdx_policy_tc_timing(buf) == 0
-names = ['loop top', 'L1 done', 'epi1 done', 'sync', 'stage ready', 'x built', 'L2 done', 'epi2 done', 'synced', 'out done']
+names = ['loop top', 'L1 done', 'a2 handed', 'x built', 'L2 done', 'epi2 done', 'synced', 'out done']
 for t in range(1, 6):
-    row = [buf[t * 16 + k] for k in range(10)]
+    row = [buf[t * 16 + k] for k in range(8)]
     base = row[0]
-    print(f'   warp0: issue L2 start={buf[t*16+10]-buf[t*16]} issued={buf[t*16+11]-buf[t*16]} L2 complete={buf[t*16+12]-buf[t*16]}')
-    print(f'tile {t}: ' + '  '.join(f'{names[k]}={row[k] - base}' for k in range(1, 10)) + f'  | next top={buf[(t + 1) * 16] - base}')
+    print(f'tile {t}: ' + '  '.join(f'{names[k]}={row[k] - base}' for k in range(1, 8)) + f'  | next top={buf[(t + 1) * 16] - base}')
