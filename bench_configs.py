@@ -60,10 +60,10 @@ def takeoff_actions(shape, dev, g):
     return -0.1 + 0.1 * torch.randn(shape, device=dev, generator=g)
 
 
-def ppo_rollout(n, T, rollouts, warmup):
+def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
     torch.manual_seed(0)
     env = VecEnv('DroneHoverBulletEnv-v0', n, seed=2, keep_final_obs=True)
-    ac = ActorCritic(env.obs_dim, device=env.device)
+    ac = ActorCritic(env.obs_dim, device=env.device, policy_kernel=policy_kernel)
     col = RolloutCollector(env, ac, T)
     for _ in range(warmup):
         data = col.collect()
@@ -80,8 +80,11 @@ def ppo_rollout(n, T, rollouts, warmup):
     ms = e0.elapsed_time(e1)
     wall = time.perf_counter() - t0
     es = data['episode_stats']
-    return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'rollout_steps': T, 'what': 'PPO rollout: policy+value forward '
-            '(torch/cuBLAS), fused env.step kernel writing into [T,N,.] buffers, GAE kernel, running-stat moments',
+    kern = {'tc': 'tcgen05 tensor-core kernel, split-TF32 (float32-level)', 'tc_tf32': 'tcgen05 tensor-core kernel, single TF32',
+            'cuda': 'CUDA-core float32 kernel'}[policy_kernel]
+    return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'rollout_steps': T, 'policy_kernel': policy_kernel,
+            'what': f'PPO rollout: fused policy step ({kern}), fused env.step kernel writing into [T,N,.] buffers, '
+                    'GAE kernel, running-stat moments',
             'env_steps_per_s': rollouts * T * n / (ms * 1e-3), 'ms_per_rollout': ms / rollouts, 'wall_s': wall,
             'episodes_in_last_rollout': es.n, 'ep_ret_mean': es.ret_mean, 'ep_len_mean': es.len_mean}
 
@@ -106,9 +109,18 @@ def main():
     p.add_argument('--scale', type=float, default=1.0, help='scale the env counts (smoke runs)')
     p.add_argument('--steps', type=int, default=20)
     p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--only', default='', help='run only the lines whose config name contains this string')
     a = p.parse_args()
     sc = lambda n: max(1024, int(n * a.scale) // 128 * 128)
     emit = lambda ln: print(json.dumps(ln), flush=True)
+    if a.only:
+        lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1, k)))
+                                        for k in ('tc', 'tc_tf32', 'cuda')],
+                 'training': lambda: emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))}
+        for name, fn in lines.items():
+            if a.only in name:
+                fn()
+        return
     emit(dict(config='configs[2] H=2', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 16, a.steps, a.warmup, uniform_actions)))
     emit(dict(config='configs[2] H=8', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 8, a.steps, a.warmup, uniform_actions,
                                                   observation_history_size=8)))
@@ -118,7 +130,8 @@ def main():
                                                            lambda s, d, g: -0.1111 + 0.05 * torch.randn(s, device=d, generator=g))))
     emit(dict(config='configs[4] env only (open loop)', **open_loop('DroneHoverBulletEnv-v0', sc(131072), 32, a.steps, a.warmup,
                                                                lambda s, d, g: 0.1111 + 0.3 * torch.randn(s, device=d, generator=g))))
-    emit(dict(config='configs[4]', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1)))
+    for k in ('tc', 'tc_tf32', 'cuda'):
+        emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1, k)))
     emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))
 
 

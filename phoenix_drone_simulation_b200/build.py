@@ -74,5 +74,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_timing():
+    """libphoenix_b200_timing.so: the same library with -DPDX_TC_TIMING (k_policy_tc records clock64
+    stamps per phase; read with pdx_policy_tc_timing, see tools/policy_tc_timing.py)."""
+    build()
+    nvcc = _nvcc()
+    obj_dir = os.path.join(HERE, 'build')
+    tobj = os.path.join(obj_dir, 'pdx_policy_tc_timing.o')
+    subprocess.run([nvcc] + ARCH + COMMON + ['-DPDX_TC_TIMING', '-c', os.path.join(CSRC, 'pdx_policy_tc.cu'), '-o', tobj], check=True)
+    objs = [os.path.join(obj_dir, u.replace('.cu', '.o')) for u in UNITS if u != 'pdx_policy_tc.cu'] + [tobj]
+    out = os.path.join(HERE, 'libphoenix_b200_timing.so')
+    subprocess.run([nvcc] + ARCH + ['-shared', '-o', out] + objs, check=True)
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--timing' in sys.argv:
+        print(build_timing())
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -84,13 +84,19 @@ def test_online_mean_std_on_device_matches_reference(name):
     np.testing.assert_allclose(oms(_cuda(g['probe'])).cpu().numpy(), g['forward'], rtol=1e-4, atol=1e-5)
 
 
-def test_fused_policy_step_matches_torch_modules():
-    """pdx_policy_step (standardise + actor MLP + critic MLP + sample + log-prob in one kernel)
-    against the torch modules that own the weights; float32, tolerance 2e-5 abs on mean / value."""
+@pytest.mark.parametrize('kernel', ['cuda', 'tc', 'tc_tf32'])
+def test_fused_policy_step_matches_torch_modules(kernel):
+    """pdx_policy_step / pdx_policy_step_tc (standardise + actor MLP + critic MLP + sample + log-prob in
+    one kernel) against the torch modules that own the weights.  'cuda' = CUDA-core float32 kernel and
+    'tc' = tcgen05 tensor-core kernel with split-TF32 operands: tolerance 2e-5 abs on mean / value;
+    'tc_tf32' = single TF32 rounding of the operands: 1e-2 abs (its documented precision)."""
     from phoenix_drone_simulation_b200.rollout import ActorCritic
     torch.manual_seed(1)
-    for obs_dim, pi_h, v_h, n in ((34, (50, 50), (64, 64), 5000), (160, (64, 64), (64, 32), 777), (17, (8, 50), (3, 64), 256)):
-        ac = ActorCritic(obs_dim, pi_hidden=pi_h, v_hidden=v_h, device='cuda', seed=3)
+    tol = dict(rtol=1e-4, atol=2e-5) if kernel != 'tc_tf32' else dict(rtol=1e-2, atol=1e-2)
+    # (160, ...) is outside the tensor-core shared-memory plan: ActorCritic falls back to the CUDA-core kernel
+    for obs_dim, pi_h, v_h, n in ((34, (50, 50), (64, 64), 5000), (160, (64, 64), (64, 32), 777), (17, (8, 50), (3, 64), 256),
+                                  (40, (64, 64), (64, 64), 128 * 300 + 1), (48, (50, 50), (64, 64), 127)):
+        ac = ActorCritic(obs_dim, pi_hidden=pi_h, v_hidden=v_h, device='cuda', seed=3, policy_kernel=kernel)
         ac.obs_oms.mean.copy_(torch.randn(obs_dim, device='cuda') * 0.3)
         ac.obs_oms.std.copy_(torch.rand(obs_dim, device='cuda') + 0.5)
         ac.set_log_std(0.7)
@@ -98,9 +104,10 @@ def test_fused_policy_step_matches_torch_modules():
         act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
         mu = torch.empty((n, 4), device='cuda')
         ac.step_into(obs, act, val, logp, mu)
+        assert ac.tc_precision == ({'cuda': 0, 'tc': 3, 'tc_tf32': 1}[kernel] if obs_dim <= 64 else 0)
         o = ac.obs_oms(obs)
-        torch.testing.assert_close(mu, ac.pi(o), rtol=1e-4, atol=2e-5)
-        torch.testing.assert_close(val, ac.v(o).squeeze(-1), rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(mu, ac.pi(o), **tol)
+        torch.testing.assert_close(val, ac.v(o).squeeze(-1), **tol)
         std = torch.exp(ac.log_std)
         ref_logp = torch.distributions.Normal(mu, std).log_prob(act).sum(-1)
         torch.testing.assert_close(logp, ref_logp, rtol=1e-4, atol=1e-4)
@@ -110,6 +117,37 @@ def test_fused_policy_step_matches_torch_modules():
         act2 = torch.empty_like(act)
         ac.step_into(obs, act2, val, logp)                      # next counter -> new draws
         assert not torch.equal(act, act2)
+
+
+def test_tensor_core_policy_draws_and_updates_follow_the_cuda_core_kernel():
+    """Both policy kernels use the same Philox counters and the same Box-Muller: for equal (seed,
+    counter) the standardised draws (a - mu) / std agree to float32 rounding.  An in-place weight update
+    must reach the packed tensor-core image (torch bumps the parameter version)."""
+    from phoenix_drone_simulation_b200.rollout import ActorCritic
+    torch.manual_seed(5)
+    n, d = 4099, 34
+    acs = {k: ActorCritic(d, device='cuda', seed=9, policy_kernel=k) for k in ('cuda', 'tc')}
+    acs['tc'].load_state_dict(acs['cuda'].state_dict())
+    obs = torch.randn((n, d), device='cuda')
+    out = {}
+    for k, ac in acs.items():
+        act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
+        mu = torch.empty((n, 4), device='cuda')
+        ac.step_into(obs, act, val, logp, mu)
+        out[k] = (act, val, logp, mu)
+    torch.testing.assert_close(out['tc'][3], out['cuda'][3], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(out['tc'][1], out['cuda'][1], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(out['tc'][0] - out['tc'][3], out['cuda'][0] - out['cuda'][3], rtol=0, atol=1e-5)
+    torch.testing.assert_close(out['tc'][2], out['cuda'][2], rtol=0, atol=1e-5)
+    ac = acs['tc']
+    with torch.no_grad():
+        for p_ in ac.pi.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))
+    act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
+    mu = torch.empty((n, 4), device='cuda')
+    ac.step_into(obs, act, val, logp, mu)
+    torch.testing.assert_close(mu, ac.pi(ac.obs_oms(obs)), rtol=1e-4, atol=2e-5)
+    assert not torch.allclose(mu, out['tc'][3], atol=1e-3)
 
 
 def test_collector_end_to_end_config5():

@@ -1,4 +1,4 @@
-"""Phase timeline of k_policy_tc (library built with -DPDX_TC_TIMING): clock64 stamps of warp 2 of CTA 0
+"""Phase timeline of k_policy_tc (python -m phoenix_drone_simulation_b200.build --timing builds the -DPDX_TC_TIMING library): clock64 stamps of warp 2 of CTA 0
 for its first eight tiles.  python tools/policy_tc_timing.py [tc|tc_tf32]"""
 import ctypes as C
 import os
