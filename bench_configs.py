@@ -4,6 +4,7 @@ bench.py (which measures configs[1], the headline).  Prints one JSON line per co
 the lines committed under profiles/ come from this script run under gpurun.
 
     python bench_configs.py [--scale 1.0] [--steps 20] [--warmup 3]
+    torchrun --nproc-per-node N ... bench_configs.py --only "configs[4]"     # configs[4] on N GPUs
 
 configs[2]  DroneCircleSimpleEnv-v0, 524,288 envs per GPU (4 Mi over 8 GPUs), H = 2 and H = 8
 configs[3]  DroneTakeOffSimpleEnv-v0, 1 Mi envs, ground effect on, obs noise, auto-reset (time limit
@@ -60,14 +61,35 @@ def takeoff_actions(shape, dev, g):
     return -0.1 + 0.1 * torch.randn(shape, device=dev, generator=g)
 
 
+def _dist():
+    """torch.distributed (NCCL) when launched under torchrun, else None.  One process per GPU."""
+    import os
+    if int(os.environ.get('WORLD_SIZE', '1')) == 1:
+        return None, 0, 1
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.pop('NCCL_DEBUG', None)
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
 def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
+    """BASELINE configs[4]: n environments PER GPU; under torchrun every rank owns its shard (env_offset) and
+    the running statistics / episode statistics are combined over NCCL inside the timed region; the
+    time is the max over ranks."""
+    dist, rank, world = _dist()
     torch.manual_seed(0)
-    env = VecEnv('DroneHoverBulletEnv-v0', n, seed=2, keep_final_obs=True)
-    ac = ActorCritic(env.obs_dim, device=env.device, policy_kernel=policy_kernel)
-    col = RolloutCollector(env, ac, T)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    env = VecEnv('DroneHoverBulletEnv-v0', n, device=dev, seed=2, keep_final_obs=True, env_offset=rank * n)
+    ac = ActorCritic(env.obs_dim, device=env.device, policy_kernel=policy_kernel, dist=dist, seed=10000 * rank)
+    col = RolloutCollector(env, ac, T, dist=dist)
     for _ in range(warmup):
         data = col.collect()
         col.update_running_statistics(data)
+    if dist:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -78,11 +100,17 @@ def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
     wall = time.perf_counter() - t0
     es = data['episode_stats']
+    n = n * world
     kern = {'tc': 'tcgen05 tensor-core kernel, split-TF32 (float32-level)', 'tc_tf32': 'tcgen05 tensor-core kernel, single TF32',
             'cuda': 'CUDA-core float32 kernel'}[policy_kernel]
-    return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'rollout_steps': T, 'policy_kernel': policy_kernel,
+    return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'n_gpus': world, 'rollout_steps': T, 'policy_kernel': policy_kernel,
             'what': f'PPO rollout: fused policy step ({kern}), fused env.step kernel writing into [T,N,.] buffers, '
                     'GAE kernel, running-stat moments',
             'env_steps_per_s': rollouts * T * n / (ms * 1e-3), 'ms_per_rollout': ms / rollouts, 'wall_s': wall,
@@ -112,7 +140,8 @@ def main():
     p.add_argument('--only', default='', help='run only the lines whose config name contains this string')
     a = p.parse_args()
     sc = lambda n: max(1024, int(n * a.scale) // 128 * 128)
-    emit = lambda ln: print(json.dumps(ln), flush=True)
+    import os
+    emit = lambda ln: print(json.dumps(ln), flush=True) if int(os.environ.get('RANK', '0')) == 0 else None
     if a.only:
         lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1, k)))
                                         for k in ('tc', 'tc_tf32', 'cuda')],
@@ -120,6 +149,8 @@ def main():
         for name, fn in lines.items():
             if a.only in name:
                 fn()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
         return
     emit(dict(config='configs[2] H=2', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 16, a.steps, a.warmup, uniform_actions)))
     emit(dict(config='configs[2] H=8', **open_loop('DroneCircleSimpleEnv-v0', sc(524288), 8, a.steps, a.warmup, uniform_actions,
