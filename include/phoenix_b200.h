@@ -112,11 +112,19 @@ typedef struct PdxConfig {
   double reserved_d[8];
 } PdxConfig;
 
+/* PdxBuffers.flags.  The step kernels are launched with programmatic stream serialisation (sm_90+):
+ * a launch may start while the kernel before it on the stream drains, and waits (griddepcontrol.wait)
+ * before it touches anything that kernel could have written.  PDX_BUF_STATE_STABLE is the caller's
+ * promise that the kernel launched immediately before this one on the stream does NOT write `state`
+ * (the collector: the policy kernel sits between two env.step launches) -- the per-env state is then
+ * loaded before the wait, under the predecessor's tail. */
+#define PDX_BUF_STATE_STABLE 1
+
 typedef struct PdxBuffers {
   int64_t n_envs;               /* environments in this shard                             */
   int64_t env_offset;           /* global index of local env 0 (RNG subsequence)          */
   int32_t device;               /* CUDA device ordinal the buffers live on                */
-  int32_t reserved;
+  int32_t flags;                /* PDX_BUF_* bits, 0 = none                               */
   void*   state;                /* [pdx_state_quads][n_envs][4] real                      */
   void*   obs;                  /* out  [n_envs][obs_dim] real, row-major                 */
   void*   reward;               /* out  [n_envs] real                (step only)          */
@@ -231,7 +239,11 @@ int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* m
  * float32-level results.  Same Philox draws as pdx_policy_step for the same (seed, counter, env).
  * Needs its own packed image (pdx_policy_tc_pack_words / pdx_policy_tc_pack; refresh after every
  * weight update).  PDX_ERR_INVALID if the shapes do not fit (hidden > 64, n_out > 4, obs_dim too
- * wide for the shared-memory plan): callers then use pdx_policy_step. */
+ * wide for the shared-memory plan): callers then use pdx_policy_step.
+ * `precision | PDX_POLICY_TC_OVERLAP`: the caller promises that the kernel launched immediately before on
+ * the stream writes none of the weight image / normaliser / log_std (the collector: an env.step launch),
+ * so the kernel stages them while that kernel drains (programmatic dependent launch). */
+#define PDX_POLICY_TC_OVERLAP 0x100
 int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision);
 int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream);
 int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,

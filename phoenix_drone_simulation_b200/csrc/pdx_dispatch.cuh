@@ -114,8 +114,18 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     smem_set[dev] = smem;
   }
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  k_rollout<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, smem, st>>>(kb);
-  return cudaGetLastError();
+  // programmatic stream serialisation: the grid may start while its predecessor drains; the kernel
+  // waits (griddepcontrol.wait) before it reads or writes anything the predecessor could touch
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = getenv("PDX_PDL") ? atoi(getenv("PDX_PDL")) : 3;     // tuning hook: bit 0 = this kernel
+  // opt-in per call (PDX_BUF_STATE_STABLE): measured, early launch of this kernel AND of a one-CTA-per-SM
+  // tensor-core policy kernel around it collapses throughput (profiles/r1_summary.md), so the caller decides
+  lc.attrs = attr; lc.numAttrs = ((pdl & 1) && (ka.b.flags & PDX_BUF_STATE_STABLE)) ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, k_rollout<T, TASK, PHYS, NOISE, RNG, PID>, kb);
 }
 
 template <class T, int TASK, int PHYS, bool PID>

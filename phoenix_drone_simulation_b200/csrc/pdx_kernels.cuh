@@ -407,6 +407,16 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
   T* state = reinterpret_cast<T*>(a.b.state);
   T* my_row0 = tile0 + (size_t)tid * D;
   T* my_row1 = tile1 + (size_t)tid * D;
+  // Programmatic dependent launch: this grid may have started while the kernel before it on the stream is
+  // still draining.  Nothing that kernel could have written is touched before griddepcontrol.wait (which
+  // returns once it has completed and its writes are visible).  With PDX_BUF_STATE_STABLE the caller
+  // guarantees that kernel does not write `state` (collector: it is the policy kernel), so the state
+  // load below runs under its tail and only the actions wait.
+  const bool state_stable = (a.b.flags & PDX_BUF_STATE_STABLE) != 0;
+  if (!state_stable) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   if (valid) {
     m.load(state, n, i);
     // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0)
@@ -426,6 +436,10 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
   // the action of step t+1 is requested while step t computes (an L2/HBM miss otherwise sits at
   // the head of every step's dependency chain)
   float4 a_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (state_stable) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   if (valid) a_next = reinterpret_cast<const float4*>(a.actions)[i];
 
   for (int t = 0; t < a.n_steps; ++t) {

@@ -36,6 +36,7 @@
 // three times the (cheap) MMA cost, which is what the parity tests pin against torch.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "../../include/phoenix_b200.h"
 
 namespace {
@@ -400,6 +401,10 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
   float* stage = reinterpret_cast<float*>(a1hi + NB * (K1 / 4) * kLboA);   // raw observation tile [128][D]
   const uint32_t bar_w = smem_u32(mbar), bar1 = bar_w + 8, bar2 = bar_w + 16, bar_x = bar_w + 24;
 
+  if (!(a.flags & 1)) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   // ---- one-time setup (all warps)
   if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   if (tid == 32) {
@@ -429,6 +434,21 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
+  // Programmatic dependent launch: everything above may run while the kernel before this one on the stream
+  // drains.  PDX_POLICY_TC_OVERLAP (flags bit 0) is the caller's promise that that kernel writes none of
+  // log_std / normaliser / weight image, which were read above / are staged below; without the promise
+  // the wait sits at the top of the kernel.  Observations are only fetched after the wait.
+  if (a.flags & 1) {
+    if (issuer && lane == 0) {         // weight image: one bulk copy, under the predecessor's tail
+      const uint32_t bytes = (uint32_t)((kCommonWords + NB * bwords) * 4);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(common)),
+                   "l"(a.packed), "r"(bytes), "r"(bar_w)
+                   : "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0;
   // a tile travels by ONE bulk copy (TMA engine) when it is complete and 16-byte aligned; the last,
   // partial tile is copied by the epilogue threads themselves
@@ -503,7 +523,7 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
     };
 
     int64_t tile = blockIdx.x;
-    if (lane == 0) {                                       // weight image: one bulk copy
+    if (lane == 0 && !(a.flags & 1)) {                     // weight image: one bulk copy
       const uint32_t bytes = (uint32_t)((kCommonWords + NB * bwords) * 4);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(common)),
@@ -714,6 +734,8 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
                                   const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, int32_t precision,
                                   uint64_t seed, uint64_t counter, float* actions, float* values, float* logp, float* mu_out,
                                   void* stream) {
+  const int32_t overlap = (precision & PDX_POLICY_TC_OVERLAP) ? 1 : 0;
+  precision &= ~PDX_POLICY_TC_OVERLAP;
   if (n <= 0 || !obs || !log_std || !packed || !actions || !values || !logp || !tc_shapes_ok(obs_dim, pi, v, precision))
     return PDX_ERR_INVALID;
   const int rc = tc_select_device_of(obs);
@@ -721,7 +743,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   const bool x3 = precision == 3;
   TcArgs a;
   a.n = n; a.obs_dim = obs_dim; a.k1 = (obs_dim + 7) & ~7; a.act_dim = pi->n_out;
-  a.flags = 0;
+  a.flags = overlap;
   a.obs = obs; a.mean = mean; a.std = std; a.eps = eps; a.log_std = log_std; a.packed = packed;
   a.seed = seed; a.counter = counter; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
   a.n_tiles = (n + kTile - 1) / kTile;
@@ -739,7 +761,16 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   // persistent CTAs: TMEM (512 columns per SM) admits one precision-3 CTA or two precision-1 CTAs per SM
   const int64_t resident = (int64_t)sms * (x3 ? 1 : ((size_t)2 * smem <= (size_t)227 * 1024 ? 2 : 1));
   const unsigned grid = (unsigned)(a.n_tiles < resident ? a.n_tiles : resident);
-  if (x3) k_policy_tc<true><<<grid, TcCfg<true>::kThreads + 32, smem, (cudaStream_t)stream>>>(a);
-  else k_policy_tc<false><<<grid, TcCfg<false>::kThreads + 32, smem, (cudaStream_t)stream>>>(a);
+  // programmatic stream serialisation: the grid may start while its predecessor drains (see the kernel)
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3((x3 ? TcCfg<true>::kThreads : TcCfg<false>::kThreads) + 32);
+  lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = getenv("PDX_PDL") ? atoi(getenv("PDX_PDL")) : 3;     // tuning hook: bit 1 = this kernel
+  lc.attrs = attr; lc.numAttrs = (pdl & 2) ? 1 : 0;
+  const cudaError_t le = x3 ? cudaLaunchKernelEx(&lc, k_policy_tc<true>, a) : cudaLaunchKernelEx(&lc, k_policy_tc<false>, a);
+  if (le != cudaSuccess) return PDX_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
 }

@@ -10,6 +10,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
 ABI_VERSION = 5
+PDX_BUF_STATE_STABLE = 1          # PdxBuffers.flags
+PDX_POLICY_TC_OVERLAP = 0x100     # or-ed into pdx_policy_step_tc's precision
 
 PDX_TASK = {'hover': 0, 'circle': 1, 'takeoff': 2}
 PDX_PHYSICS = {'SimplePhysics': 0, 'PyBulletPhysics': 1}
@@ -54,7 +56,7 @@ class PdxConfig(C.Structure):
 
 class PdxBuffers(C.Structure):
     _fields_ = [
-        ('n_envs', C.c_int64), ('env_offset', C.c_int64), ('device', C.c_int32), ('reserved', C.c_int32),
+        ('n_envs', C.c_int64), ('env_offset', C.c_int64), ('device', C.c_int32), ('flags', C.c_int32),
         ('state', C.c_void_p), ('obs', C.c_void_p), ('reward', C.c_void_p), ('cost', C.c_void_p),
         ('terminated', C.c_void_p), ('truncated', C.c_void_p), ('final_obs', C.c_void_p),
         ('episode_return', C.c_void_p), ('episode_length', C.c_void_p), ('episode_stats', C.c_void_p),

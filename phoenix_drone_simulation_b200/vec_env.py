@@ -164,14 +164,18 @@ class VecEnv:
         return self.obs, self.reward, self.terminated, self.truncated, info
 
     # ---- prepared launches: everything that does not change between calls is built once ------
-    def prepare_step(self, actions, out):
+    def prepare_step(self, actions, out, state_stable=False):
         """Returns a handle for `step_prepared`: the PdxBuffers of a step that reads `actions`
-        [N, 4] and writes into the tensors of `out` (see `step`).  The tensors must stay alive."""
+        [N, 4] and writes into the tensors of `out` (see `step`).  The tensors must stay alive.
+        state_stable: promise that the kernel launched right before each use of this handle does not
+        write this VecEnv's state (PDX_BUF_STATE_STABLE: the state load overlaps that kernel's tail)."""
         assert actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, 4)
         buf = _lib.PdxBuffers.from_buffer_copy(self._buf)
         for k, t in out.items():
             assert t.is_cuda and t.is_contiguous() and t.shape[0] == self.num_envs, k
             setattr(buf, k, t.data_ptr())
+        if state_stable:
+            buf.flags |= _lib.PDX_BUF_STATE_STABLE
         return (C.byref(self.pdx), C.byref(buf), C.c_void_p(actions.data_ptr()), buf, actions, out)
 
     def step_prepared(self, handle, stream):
