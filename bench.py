@@ -299,6 +299,35 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def ppo_rollout_leg(dev, n=131072, T=64, rollouts=3):
+    """BASELINE.json configs[4] next to the headline: DroneHoverBulletEnv-v0 driving a PPO rollout on this
+    GPU -- tcgen05 tensor-core policy step, fused env.step kernel, GAE and running statistics, all on
+    device (bench_configs.py measures the same per policy kernel and under torchrun)."""
+    import torch
+    from phoenix_drone_simulation_b200 import VecEnv
+    from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
+    torch.manual_seed(0)
+    env = VecEnv('DroneHoverBulletEnv-v0', n, device=dev, seed=2, keep_final_obs=True)
+    ac = ActorCritic(env.obs_dim, device=dev)
+    col = RolloutCollector(env, ac, T)
+    col.update_running_statistics(col.collect())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rollouts):
+        data = col.collect()
+        col.update_running_statistics(data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {'workload': f'DroneHoverBulletEnv-v0, {n} envs x {T} steps per rollout, reference PPO networks (pi 50-50 relu, '
+                        'v 64-64 tanh): policy step + env.step + GAE + running statistics (BASELINE.json configs[4])',
+            'value': rollouts * T * n / (ms * 1e-3), 'unit': UNIT, 'ms_per_rollout': ms / rollouts,
+            'policy_kernel': {3: 'k_policy_tc (tcgen05, split TF32)', 1: 'k_policy_tc (tcgen05, single TF32)',
+                              0: 'k_policy (CUDA cores)'}[ac.tc_precision],
+            'gpu_launches_per_rollout': 2 * T + 3}
+
+
 class DistCtx:
     def __init__(self, n_gpus):
         import torch
@@ -448,6 +477,11 @@ def run_gpu_arm(a):
             'us_per_launch': usl, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
             'env_steps_per_s': kl * inner_l * nl / (msl * 1e-3)}
         del big, segl
+    if ctx.world == 1 and not a.no_ppo_rollout:
+        try:
+            extra['ppo_rollout'] = ppo_rollout_leg(dev)
+        except Exception as e:                       # never lose the headline line to the companion leg
+            extra['ppo_rollout'] = {'error': repr(e)[:200]}
 
     episodes = int(ctx.episodes.item()) if ctx.dist else int(env.episode_stats()[0].item())
     ctx.close()
@@ -481,6 +515,7 @@ def main():
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--e2e-div', type=int, default=4, help='e2e leg times steps/e2e_div segments')
     p.add_argument('--large-envs', type=int, default=4 * 1024 * 1024)
+    p.add_argument('--no-ppo-rollout', action='store_true', help='skip the configs[4] companion leg')
     a = p.parse_args()
     if a.impl == 'reference':
         run_reference_arm(a)

@@ -148,6 +148,14 @@ def test_tensor_core_policy_draws_and_updates_follow_the_cuda_core_kernel():
     ac.step_into(obs, act, val, logp, mu)
     torch.testing.assert_close(mu, ac.pi(ac.obs_oms(obs)), rtol=1e-4, atol=2e-5)
     assert not torch.allclose(mu, out['tc'][3], atol=1e-3)
+    # an observation buffer that is only 4-byte aligned: no TMA bulk copies, the epilogue warps stage the tiles
+    flat = torch.empty(n * d + 1, device='cuda')
+    obs_u = flat[1:].view(n, d)
+    obs_u.copy_(obs)
+    assert obs_u.data_ptr() % 16 == 4 and obs_u.is_contiguous()
+    mu_u = torch.empty_like(mu)
+    ac.step_into(obs_u, act, val, logp, mu_u)
+    torch.testing.assert_close(mu_u, mu, rtol=0, atol=0)
 
 
 def test_collector_end_to_end_config5():
