@@ -137,14 +137,15 @@ def main():
     p.add_argument('--scale', type=float, default=1.0, help='scale the env counts (smoke runs)')
     p.add_argument('--steps', type=int, default=20)
     p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--kernels', default='tc,tc_tf32,cuda', help='policy kernels of the configs[4] lines, in this order')
     p.add_argument('--only', default='', help='run only the lines whose config name contains this string')
     a = p.parse_args()
     sc = lambda n: max(1024, int(n * a.scale) // 128 * 128)
     import os
     emit = lambda ln: print(json.dumps(ln), flush=True) if int(os.environ.get('RANK', '0')) == 0 else None
     if a.only:
-        lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1, k)))
-                                        for k in ('tc', 'tc_tf32', 'cuda')],
+        lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 3, k)))
+                                        for k in a.kernels.split(',')],
                  'training': lambda: emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))}
         for name, fn in lines.items():
             if a.only in name:
@@ -161,8 +162,8 @@ def main():
                                                            lambda s, d, g: -0.1111 + 0.05 * torch.randn(s, device=d, generator=g))))
     emit(dict(config='configs[4] env only (open loop)', **open_loop('DroneHoverBulletEnv-v0', sc(131072), 32, a.steps, a.warmup,
                                                                lambda s, d, g: 0.1111 + 0.3 * torch.randn(s, device=d, generator=g))))
-    for k in ('tc', 'tc_tf32', 'cuda'):
-        emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 1, k)))
+    for k in a.kernels.split(','):
+        emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 3, k)))
     emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))
 
 
