@@ -359,6 +359,12 @@ __device__ __forceinline__ void output_epilogue(uint32_t taddr, int cg, const fl
     } else {
       tmem_wait_ld();
     }
+    float wc[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {                       // ca is a multiple of 16: 128-bit broadcast loads
+      const float4 t = *reinterpret_cast<const float4*>(w3c + ca + 4 * j4);
+      wc[4 * j4] = t.x; wc[4 * j4 + 1] = t.y; wc[4 * j4 + 2] = t.z; wc[4 * j4 + 3] = t.w;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float ya = fmaxf(__uint_as_float(ra[j]), 0.0f);
@@ -369,7 +375,7 @@ __device__ __forceinline__ void output_epilogue(uint32_t taddr, int cg, const fl
       part[1] = fmaf(ya, w.y, part[1]);
       part[2] = fmaf(ya, w.z, part[2]);
       part[3] = fmaf(ya, w.w, part[3]);
-      part[4] = fmaf(yc, w3c[ca + j], part[4]);
+      part[4] = fmaf(yc, wc[j], part[4]);
     }
   }
 }
@@ -620,6 +626,20 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
       // so the X buffer is free)
       if (next < a.n_tiles) build_x(next, par ^ 1);
       TC_STAMP(3);
+      // the Gaussian draw does not depend on the networks: do it now, while layer 2 runs, instead of on the
+      // critical path after the last epilogue.  Same Philox counters as k_policy: identical draws for the
+      // same (seed, counter, env).
+      float eps[4] = {0.f, 0.f, 0.f, 0.f}, lp = 0.0f;
+      if (cg == 0) {
+        const int64_t i = env0 + row;
+        const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
+        pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < a.act_dim) lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
+      }
       // ---- layer 2 done -> activation, layer 3 partial dot products
       mbar_wait(bar2, par);
       tc_fence_after();
@@ -648,21 +668,10 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
             mu[0] += p0.x; mu[1] += p0.y; mu[2] += p0.z; mu[3] += p0.w;
             v += src[1].x;
           }
-          // same Philox counters as k_policy: identical draws for the same (seed, counter, env)
-          const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
-                                     make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-          float eps[4];
-          pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
-          pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
-          float lp = 0.0f;
           float av[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < a.act_dim) {
-              av[k] = fmaf(act_std[k], eps[k], mu[k]);
-              lp += -0.5f * eps[k] * eps[k] - act_std[4 + k] - 0.9189385332046727f;
-            }
-          }
+          for (int k = 0; k < 4; ++k)
+            if (k < a.act_dim) av[k] = fmaf(act_std[k], eps[k], mu[k]);
           reinterpret_cast<float4*>(a.act)[i] = make_float4(av[0], av[1], av[2], av[3]);
           a.val[i] = v;
           a.logp[i] = lp;
