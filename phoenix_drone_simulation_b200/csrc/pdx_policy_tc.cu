@@ -757,15 +757,17 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   a.seed = seed; a.counter = counter; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
   a.n_tiles = (n + kTile - 1) / kTile;
   const size_t smem = tc_smem_bytes(a.k1, obs_dim, x3);
-  static size_t set[2] = {0, 0};
-  if (smem > set[x3]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static size_t set_by_dev[2][64] = {};              // opt-in dynamic shared memory, per device and variant
+  size_t& set_ref = set_by_dev[x3][dev & 63];
+  if (smem > set_ref) {
     const cudaError_t e = x3 ? cudaFuncSetAttribute(k_policy_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                              : cudaFuncSetAttribute(k_policy_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return PDX_ERR_CUDA;
-    set[x3] = smem;
+    set_ref = smem;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
+  int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // persistent CTAs: TMEM (512 columns per SM) admits one precision-3 CTA or two precision-1 CTAs per SM
   const int64_t resident = (int64_t)sms * (x3 ? 1 : ((size_t)2 * smem <= (size_t)227 * 1024 ? 2 : 1));
