@@ -232,7 +232,8 @@ int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* m
                     const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
                     uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
 
-/* The same ActorCritic.step on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators
+/* The same ActorCritic.step (algs/core.py:370-393; MLPGaussianActor core.py:227-289, MLPCritic core.py:297-310,
+ * standardisation utils/online_mean_std.py:42-48) on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators
  * and hidden activations in tensor memory; csrc/pdx_policy_tc.cu).  128 environments per tile, one
  * persistent CTA per SM (two for precision 1).  `precision`: 1 = operands rounded to TF32 once
  * (~1e-3 relative error on mu / value), 3 = split-TF32 (hi + lo operands, three products per term):
