@@ -426,3 +426,32 @@ def test_checkpoint_resume_is_exact():
         o, r, te, tr, _ = other.step(acts[T + t])
         assert torch.equal(o, ref[t][0]) and torch.equal(r, ref[t][1]) and torch.equal(te, ref[t][2]) and torch.equal(tr, ref[t][3])
     assert torch.equal(other.episode_stats(), ref_stats)
+
+
+@pytest.mark.gpu
+def test_early_launch_promise_does_not_change_results():
+    """PDX_BUF_STATE_STABLE (programmatic dependent launch: the state is loaded before the dependency wait)
+    only moves work under the predecessor's tail.  Prepared steps with the flag, interleaved with a kernel
+    that writes the action tensor on the same stream (the collector's pattern), are bit-identical to plain
+    steps."""
+    import ctypes as C
+    N, T = 4099, 12
+    for env_id in ('DroneHoverSimpleEnv-v0', 'DroneHoverBulletEnv-v0'):
+        a = _vec(env_id, N, seed=4)
+        b = _vec(env_id, N, seed=4)
+        assert torch.equal(a.reset(), b.reset())
+        g = torch.Generator(device='cuda').manual_seed(8)
+        acts = (a.cfg.hover_action + 0.4 * torch.randn((T, N, 4), device='cuda', generator=g)).contiguous()
+        live = torch.zeros((N, 4), device='cuda')           # written right before every flagged launch
+        out = {'obs': torch.zeros((N, b.obs_dim), device='cuda'), 'reward': torch.zeros(N, device='cuda'),
+               'cost': torch.zeros(N, device='cuda'), 'terminated': torch.zeros(N, dtype=torch.uint8, device='cuda'),
+               'truncated': torch.zeros(N, dtype=torch.uint8, device='cuda')}
+        handle = b.prepare_step(live, out, state_stable=True)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for t in range(T):
+            o, r, te, tr, _ = a.step(acts[t])
+            live.copy_(acts[t])                             # the "policy kernel": produces the actions, leaves the state alone
+            b.step_prepared(handle, stream)
+            assert torch.equal(o, out['obs']) and torch.equal(r, out['reward']), (env_id, t)
+            assert torch.equal(te, out['terminated'].bool()) and torch.equal(tr, out['truncated'].bool())
+        assert torch.equal(a.state, b.state)
