@@ -105,3 +105,45 @@ def statistics_scalar(per_rank_values):
     mn = min(float(np.min(x)) if len(x) else np.inf for x in xs)
     mx = max(float(np.max(x)) if len(x) else -np.inf for x in xs)
     return mean, std, mn, mx
+
+
+# ---------------------------------------------------------------------------------------------
+#  ActorCritic.step (algs/core.py:370-393), deterministic part, float64
+# ---------------------------------------------------------------------------------------------
+def mlp_forward(x, layers, activation):
+    """build_mlp_network (utils/utils.py:56-110) / core.build_mlp_network: Linear layers with `activation`
+    between them and identity after the last.  layers: [(W [out][in], b [out]), ...]."""
+    act = {'relu': lambda z: np.maximum(z, 0.0), 'tanh': np.tanh}[activation]
+    h = np.asarray(x, dtype=np.float64)
+    for k, (w, b) in enumerate(layers):
+        h = h @ np.asarray(w, dtype=np.float64).T + np.asarray(b, dtype=np.float64)
+        if k + 1 < len(layers):
+            h = act(h)
+    return h
+
+
+def actor_critic_step(obs, mean, std, pi_layers, v_layers, log_std, eps_draw, norm_eps=1e-5):
+    """ActorCritic.step for a batch: standardise (utils/online_mean_std.py:42-48), v = critic(o) (tanh MLP,
+    core.py:297-310), mu = actor(o) (relu MLP, core.py:227-289), a = mu + exp(log_std) * eps (core.py:282-289
+    with the N(0,1) draw supplied), log p = sum log N(a; mu, std) (core.py:254-262).
+    Returns (action, value, logp, mu)."""
+    o = (np.asarray(obs, dtype=np.float64) - np.asarray(mean, dtype=np.float64)) / (np.asarray(std, dtype=np.float64) + norm_eps)
+    mu = mlp_forward(o, pi_layers, 'relu')
+    v = mlp_forward(o, v_layers, 'tanh')[:, 0] if v_layers is not None else None
+    sd = np.exp(np.asarray(log_std, dtype=np.float64))
+    a = mu + sd * eps_draw
+    logp = (-0.5 * ((a - mu) / sd) ** 2 - np.log(sd) - 0.5 * np.log(2.0 * np.pi)).sum(-1)
+    return a, v, logp, mu
+
+
+def load_policy_json_layers(path):
+    """The JSON policy format (utils/utils.py:362-430 dump_network_json): scaling parameters and dense layers."""
+    import json
+    with open(path) as f:
+        data = json.load(f)
+    layers = []
+    while str(len(layers)) in data:
+        e = data[str(len(layers))]
+        layers.append((np.asarray(e['weights'], dtype=np.float64), np.asarray(e['biases'], dtype=np.float64).reshape(-1)))
+    sp = np.asarray(data['scaling_parameters'], dtype=np.float64)
+    return sp[0], sp[1], layers, data.get('activation', 'relu')

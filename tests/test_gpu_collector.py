@@ -158,6 +158,34 @@ def test_tensor_core_policy_draws_and_updates_follow_the_cuda_core_kernel():
     torch.testing.assert_close(mu_u, mu, rtol=0, atol=0)
 
 
+@pytest.mark.parametrize('kernel', ['cuda', 'tc'])
+def test_policy_kernels_match_the_numpy_oracle(kernel):
+    """Both policy kernels against oracle.actor_critic_step (float64 numpy restatement of ActorCritic.step,
+    pinned to the reference loader's golden): mean, value, and -- replaying the draw the kernel made --
+    action and log-probability.  float32 kernels: 2e-5 abs."""
+    from phoenix_drone_simulation_b200.rollout import ActorCritic
+    torch.manual_seed(11)
+    n, d = 3000, 34
+    ac = ActorCritic(d, device='cuda', seed=2, policy_kernel=kernel)
+    ac.obs_oms.mean.copy_(torch.randn(d, device='cuda') * 0.2)
+    ac.obs_oms.std.copy_(torch.rand(d, device='cuda') + 0.5)
+    ac.set_log_std(0.6)
+    obs = torch.randn((n, d), device='cuda') * 1.5
+    act = torch.empty((n, 4), device='cuda'); val = torch.empty(n, device='cuda'); logp = torch.empty(n, device='cuda')
+    mu = torch.empty((n, 4), device='cuda')
+    ac.step_into(obs, act, val, logp, mu)
+    layers = lambda net: [(m.weight.detach().cpu().numpy(), m.bias.detach().cpu().numpy()) for m in net if isinstance(m, torch.nn.Linear)]
+    log_std = ac.log_std.detach().cpu().numpy()
+    draw = ((act - mu) / torch.exp(ac.log_std)).cpu().numpy().astype(np.float64)      # the standardised draw the kernel used
+    a_o, v_o, lp_o, mu_o = co.actor_critic_step(obs.cpu().numpy(), ac.obs_oms.mean.cpu().numpy(), ac.obs_oms.std.cpu().numpy(),
+                                                layers(ac.pi), layers(ac.v), log_std, draw, norm_eps=ac.obs_oms.eps)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_o, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(val.cpu().numpy(), v_o, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(act.cpu().numpy(), a_o, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(logp.cpu().numpy(), lp_o, rtol=1e-4, atol=1e-4)
+    assert abs(draw.mean()) < 0.05 and abs(draw.std() - 1) < 0.05
+
+
 def test_collector_end_to_end_config5():
     """BASELINE config 5: DroneHoverBulletEnv-v0 driving a PPO rollout (reference networks), all on
     device.  Checks the stored fields against an independent recomputation."""
