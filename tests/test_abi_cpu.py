@@ -172,3 +172,14 @@ def test_tensor_core_policy_shape_checks_need_no_device(lib):
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(mlp(64, 64, 2)), 3) == -1
     assert lib.pdx_policy_step_tc(0, 34, None, None, None, 0.0, C.byref(pi), C.byref(v), None, None, 3, 0, 0,
                                   None, None, None, None, None) == -1
+
+
+def test_flag_constants_match_the_header():
+    """lib.py mirrors the #define'd flag bits of include/phoenix_b200.h (and the struct field they live in)."""
+    import re
+    header = open(os.path.join(ROOT, 'include', 'phoenix_b200.h')).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r'#define\s+(PDX_[A-Z_]+)\s+(0x[0-9a-fA-F]+|\d+)\s*$', header, re.M)}
+    assert defs['PDX_BUF_STATE_STABLE'] == L.PDX_BUF_STATE_STABLE
+    assert defs['PDX_POLICY_TC_OVERLAP'] == L.PDX_POLICY_TC_OVERLAP
+    assert 'flags' in [f[0] for f in L.PdxBuffers._fields_] and 'int32_t flags;' in header
+    assert L.PDX_POLICY_TC_OVERLAP & 3 == 0          # must not collide with the precision values 1 and 3
