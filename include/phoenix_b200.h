@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PDX_ABI_VERSION 5
+#define PDX_ABI_VERSION 6
 
 typedef enum PdxStatus {
   PDX_OK = 0,

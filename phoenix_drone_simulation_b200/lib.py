@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 PDX_BUF_STATE_STABLE = 1          # PdxBuffers.flags
 PDX_POLICY_TC_OVERLAP = 0x100     # or-ed into pdx_policy_step_tc's precision
 
