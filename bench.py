@@ -9,11 +9,14 @@ Workload (BASELINE.json configs[1], SURVEY.md 8d "Config 2"): DroneHoverSimpleEn
 65,536 lock-step environments per GPU, 10 % domain randomisation, observation noise on,
 history H = 2, float32 SoA state, on-device Philox, U(-1,1) float32 actions, auto-reset.
 
-One bench "step" = one rollout segment of `--inner` (default 64) env.steps of every
-environment, written into [inner, N, .] rollout tensors.  Actions and observations stream
-through ring buffers larger than L2; the 65,536-env state itself (~13 MB) is L2-resident by the
-workload's definition -- `config.l2` says so, and `roofline_hbm_resident_off` repeats the
-measurement at 4 Mi environments per GPU where the state (0.9 GB) cannot stay in L2.
+One bench "step" = `--launches` (default 16) rollout segments of `--inner` (default 64) env.steps
+of every environment = 1,024 env.steps per environment, each segment ONE fused launch writing
+into [inner, N, .] rollout tensors.  Actions and observations stream through ring buffers larger
+than L2; the 65,536-env state itself (~13 MB) is L2-resident by the workload's definition --
+`config.l2` says so, and `roofline_hbm_resident_off` repeats the measurement at 4 Mi environments
+per GPU where the state (0.9 GB) cannot stay in L2.  Multi-GPU: the episode statistics of a bench
+step are combined across ranks ONCE per step (the reference reduces them once per epoch,
+utils/loggers.py:519-524) with an asynchronous NCCL all-gather that overlaps the next step.
 
 JSON keys follow the driver contract: value (device-resident inputs, CUDA events, max over
 ranks), e2e (host buffers, H2D/D2H inside the timed region), roofline, cpu_baseline, clocks,
@@ -156,17 +159,21 @@ class ClockSampler:
     def _loop(self):
         while not self.stop_flag:
             self.sample_once()
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         if self.nv is not None:
             self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
 
-    def stop(self):
+    def halt(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join()
+            self.thread = None
+
+    def stop(self):
+        self.halt()
         s = sorted(self.samples)
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
                 'reasons': sorted(self.reasons), 'samples': len(s)}
@@ -175,8 +182,9 @@ class ClockSampler:
 def workload_config(a, n_per_gpu):
     return {'workload': f'{a.env_id}, {n_per_gpu} lock-step envs per GPU, DR 0.10, observation noise on, '
                         f'H=2, U(-1,1) actions, auto-reset (BASELINE.json configs[1])',
-            'env_id': a.env_id, 'envs_per_gpu': n_per_gpu, 'env_steps_per_bench_step': a.inner * n_per_gpu,
-            'inner_env_steps': a.inner, 'launch': a.mode, 'rng': 'philox4x32-10 on device',
+            'env_id': a.env_id, 'envs_per_gpu': n_per_gpu, 'env_steps_per_bench_step': a.launches * a.inner * n_per_gpu,
+            'inner_env_steps': a.inner, 'launches_per_bench_step': a.launches, 'launch': a.mode,
+            'rng': 'philox4x32-10 on device',
             'l2': 'actions and observations stream through ring buffers larger than L2; the per-env state '
                   'is L2-resident at this size by the workload definition (see roofline_hbm_resident_off)'}
 
@@ -221,27 +229,33 @@ def ring_slots(bytes_per_segment):
     return max(2, -(-2 * L2_BYTES // bytes_per_segment))
 
 
-def time_device(env, seg, K, W, dist_ctx, sampler=None):
-    """K segments timed with CUDA events on the launching stream; max over ranks.  `sampler`: clocks
-    are also read from this thread while the device works through the queued launches, so even a
-    very short timed region is sampled under load."""
+def time_device(env, seg, K, W, dist_ctx, sampler=None, per_step=1):
+    """K bench steps of `per_step` segments each, timed with CUDA events on the launching stream; max
+    over ranks.  `sampler`: clocks are read ONLY between the two events (the sampler thread is started
+    after the first and this thread keeps sampling until the second has completed)."""
     import torch
     launches = 0
-    for k in range(W):
+    for k in range(W * per_step):
         seg.run(k)
-        dist_ctx.reduce_stats(env)
+        if (k + 1) % per_step == 0:
+            dist_ctx.reduce_stats(env)
+    dist_ctx.flush_stats()
     dist_ctx.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(K):
-        launches += seg.run(W + k)
-        dist_ctx.reduce_stats(env)
+    if sampler is not None:
+        sampler.start()
+    for k in range(K * per_step):
+        launches += seg.run(W * per_step + k)
+        if (k + 1) % per_step == 0:
+            dist_ctx.reduce_stats(env)
+    dist_ctx.flush_stats()
     e1.record()
     if sampler is not None:
-        sampler.sample_once()
         while not e1.query():
-            sampler.sample_once()
+            time.sleep(0.0005)
+        sampler.halt()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     dist_ctx.barrier()
@@ -341,16 +355,17 @@ class DistCtx:
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-            # keep stdout to ONE JSON line: NCCL prints its version banner there at any debug level
-            os.environ.pop('NCCL_DEBUG', None)
-            if os.environ.get('PDX_NCCL_DEBUG'):
-                os.environ['NCCL_DEBUG'] = os.environ['PDX_NCCL_DEBUG']
+            # The caller's NCCL_DEBUG is left alone (the driver reads NCCL's rank / topology lines).  stdout
+            # carries ONE JSON line, so NCCL's log goes to stderr unless the caller chose a file.
+            if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+                os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
             dist.init_process_group('nccl', device_id=self.device)
             self.dist = dist
         else:
             self.dist = None
         import torch as _t
         self.episodes = _t.zeros((), dtype=_t.float64, device=self.device)   # finished episodes, all ranks
+        self._pending = None
 
     def barrier(self):
         if self.dist:
@@ -365,20 +380,51 @@ class DistCtx:
         return float(t.item())
 
     def reduce_stats(self, env):
-        """Episode-return statistics all-reduce: the only cross-GPU traffic of the path, once per
-        rollout segment (replaces utils/mpi_tools.py:217-240)."""
+        """Episode-return statistics across ranks: the only cross-GPU traffic of the path, once per
+        bench step (replaces utils/mpi_tools.py:217-240, which the reference runs once per
+        epoch, utils/loggers.py:519-524).  The all-gather is asynchronous (NCCL's own stream); its result
+        is combined one step later, so the collective never sits between two env.step launches."""
         if not self.dist:
             return
-        from phoenix_drone_simulation_b200.rollout import allreduce_episode_stats
-        # this segment's statistics only (the collector's flow: roll out, combine, log, clear) --
-        # re-reducing the running total in place would count every earlier segment `world` times
-        seg_stats = env.episode_stats(clear=True)
-        allreduce_episode_stats(seg_stats, self.dist)
-        self.episodes.add_(seg_stats[0])
+        from phoenix_drone_simulation_b200.rollout import gather_episode_stats_async
+        self.flush_stats()
+        # this step's statistics only (the collector's flow: roll out, combine, log, clear)
+        self._pending = gather_episode_stats_async(env.episode_stats(clear=True), self.dist)
+
+    def flush_stats(self):
+        if self._pending is not None:
+            self.episodes.add_(self._pending()[0])
+            self._pending = None
 
     def close(self):
         if self.dist:
             self.dist.destroy_process_group()
+
+
+def kernel_source_hash():
+    """sha256 over the sources the step kernel is compiled from: ties profile counters to a build."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, 'phoenix_drone_simulation_b200', 'csrc')
+    for f in ('pdx_kernels.cuh', 'pdx_model.cuh', 'pdx_math.cuh', 'pdx_layout.h', 'pdx_dispatch.cuh'):
+        with open(os.path.join(csrc, f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def profile_counters(env_steps_per_launch):
+    """Per-launch ncu counters of the bench's step kernel (profiles/rollout_counters.json, written by
+    profiles/export_summary.py from an `ncu --set full` capture of this command).  `stale` = the kernel
+    sources changed since the capture (the counts then describe an older build)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'rollout_counters.json')) as f:
+            c = json.load(f)
+        if c['env_steps_per_launch'] != env_steps_per_launch:
+            return None
+        c['stale'] = c.get('source_hash') != kernel_source_hash()
+        return c
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -414,40 +460,48 @@ def run_gpu_arm(a):
     seg = Segment(env, a.inner, ring_slots(seg_bytes), gen, a.mode)
 
     sampler = ClockSampler(ctx.local_rank)
-    sampler.start()
-    ms, launches = time_device(env, seg, a.steps, a.warmup, ctx, sampler)
+    ms, launches = time_device(env, seg, a.steps, a.warmup, ctx, sampler, per_step=a.launches)
     clocks = sampler.stop()
-    env_steps = a.steps * a.inner * n * ctx.world
+    env_steps = a.steps * a.launches * a.inner * n * ctx.world
     value = env_steps / (ms * 1e-3)
 
-    # roofline of the dominant kernel (the fused step): algorithmic bytes per launch / mean duration
+    # roofline of the dominant kernel (the fused step).  The kernel is bound by ISSUE SLOTS, not by HBM:
+    #   achieved = warp instructions per launch (ncu smsp__inst_executed.sum of this very launch shape, read
+    #              from profiles/ together with the hash of the kernel sources it was captured from)
+    #              / mean launch duration measured here with CUDA events
+    #   peak     = SMs x 4 schedulers x SM clock under load (one warp instruction per scheduler and cycle)
+    # The HBM view of the same launch (algorithmic bytes / duration against the measured copy bandwidth)
+    # is reported next to it under `hbm`.
     peak, peak_src = measured_peak()
-    steps_per_launch = a.steps * a.inner // launches
+    steps_per_launch = a.steps * a.launches * a.inner // launches
     bytes_per_launch = env.rollout_bytes(steps_per_launch) * n
     us_per_launch = ms * 1e3 / launches
     achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
-    traffic = None
-    try:                      # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this launch shape
-        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-            tj = json.load(f)
-        if tj['env_steps_per_launch'] == steps_per_launch * n:
-            traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
-    except Exception:
-        pass
-    # issue-slot view of the same kernel (it is issue-bound, not HBM-bound): warp instructions per
-    # warp-step from the same ncu capture, against schedulers x clock
+    counters = profile_counters(steps_per_launch * n)
     props = torch.cuda.get_device_properties(dev)
-    issue_peak = props.multi_processor_count * 4 * (clocks['sm_mhz'] or 1965) * 1e6
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'algorithmic_bytes_per_launch': bytes_per_launch,
-                'issue': {'warp_inst_per_warp_step': 2229, 'source': 'profiles/r1_rollout_final_64k.summary.csv',
-                          'achieved_warp_inst_per_s': value / ctx.world / 32 * 2229, 'peak_warp_inst_per_s': issue_peak,
-                          'frac': value / ctx.world / 32 * 2229 / issue_peak}, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
-                'env_steps_per_launch': steps_per_launch * n, 'bytes_per_env_step': bytes_per_launch / (steps_per_launch * n),
-                'us_per_launch': us_per_launch, 'peak_source': peak_src}
+    sm_mhz = clocks['sm_mhz'] or 1965
+    issue_peak = props.multi_processor_count * 4 * sm_mhz * 1e6
+    hbm = {'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+           'algorithmic_bytes_per_launch': bytes_per_launch,
+           'bytes_per_env_step': bytes_per_launch / (steps_per_launch * n)}
+    if counters:
+        inst = counters['smsp__inst_executed.sum']
+        ach_i = inst / (us_per_launch * 1e-6)
+        roofline = {'bound': 'issue', 'achieved': ach_i / 1e9, 'peak': issue_peak / 1e9, 'unit': 'G warp-inst/s',
+                    'frac': ach_i / issue_peak, 'traffic': counters['dram_bytes_read'] + counters['dram_bytes_write'],
+                    'warp_inst_per_launch': inst, 'warp_inst_per_warp_step': inst / (steps_per_launch * n / 32),
+                    'counters_source': counters['source'], 'counters_stale': counters['stale'],
+                    'peak_source': f'{props.multi_processor_count} SMs x 4 schedulers x {sm_mhz} MHz (median SM clock under load)'}
+    else:
+        roofline = dict(hbm, bound='hbm', traffic=None)
+    roofline.update({'hbm': hbm, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
+                     'env_steps_per_launch': steps_per_launch * n, 'us_per_launch': us_per_launch})
 
-    e2e_ms, h2d, d2h = time_e2e(env, a.inner, max(1, a.steps // a.e2e_div), a.warmup, ctx, 99 + ctx.rank)
-    e2e_steps = max(1, a.steps // a.e2e_div) * a.inner * n * ctx.world
+    # e2e: one bench step = the same a.launches x a.inner env.steps per environment, in 8-step chunks
+    e2e_k = max(1, a.steps // a.e2e_div)
+    e2e_ms, h2d, d2h = time_e2e(env, a.inner, e2e_k * a.launches, min(a.warmup, 3), ctx, 99 + ctx.rank)
+    h2d, d2h = h2d * a.launches, d2h * a.launches
+    e2e_steps = e2e_k * a.launches * a.inner * n * ctx.world
     e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'numa_node_rank0': ctx.numa_node,
            'api': 'VecEnv.step_many_host: pinned host action/obs/reward/cost/flag buffers, H2D + launch + D2H per 8-step chunk on three streams, all inside the timed region'}
@@ -457,8 +511,9 @@ def run_gpu_arm(a):
         # the other action distribution SURVEY 8d asks for: a near-hover fixed policy (fewer resets)
         seg.actions = None
         segh = Segment(env, a.inner, ring_slots(seg_bytes), gen, a.mode, near_hover=True)
-        msh, _ = time_device(env, segh, max(10, a.steps // 2), a.warmup, ctx)
-        extra['fixed_policy'] = {'actions': 'HOVER_ACTION + N(0, 0.05)', 'value': max(10, a.steps // 2) * a.inner * n / (msh * 1e-3),
+        kh = max(2, a.steps // 4)
+        msh, _ = time_device(env, segh, kh, min(a.warmup, 2), ctx, per_step=a.launches)
+        extra['fixed_policy'] = {'actions': 'HOVER_ACTION + N(0, 0.05)', 'value': kh * a.launches * a.inner * n / (msh * 1e-3),
                                  'unit': UNIT}
         del segh
     if a.large_envs and ctx.world == 1:
@@ -490,7 +545,7 @@ def run_gpu_arm(a):
         return
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
-        'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms / a.steps, 'timed_region_ms': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a, n),
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
         'episodes_finished': episodes,
@@ -504,7 +559,8 @@ def run_gpu_arm(a):
 def main():
     p = argparse.ArgumentParser()
     p.add_argument('--gpus', type=int, default=1)
-    p.add_argument('--steps', type=int, default=400)
+    p.add_argument('--steps', type=int, default=20)
+    p.add_argument('--launches', type=int, default=16, help='fused launches (rollout segments) per bench step')
     p.add_argument('--warmup', type=int, default=5)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--env-id', default=ENV_ID)

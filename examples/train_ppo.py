@@ -35,7 +35,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.pop('NCCL_DEBUG', None)
+        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'     # stdout carries the JSON lines
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from phoenix_drone_simulation_b200.ppo import PPO
     alg = PPO(a.env, num_envs=a.num_envs, steps=a.steps, epochs=a.epochs, device=f'cuda:{local}', seed=a.seed, dist=dist)

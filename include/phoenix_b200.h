@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PDX_ABI_VERSION 6
+#define PDX_ABI_VERSION 7
 
 typedef enum PdxStatus {
   PDX_OK = 0,
@@ -200,10 +200,13 @@ int pdx_dump_draws(const PdxConfig* cfg, const PdxBuffers* buf, const float* act
  * quirk that also scales the appended bootstrap value).  All float32.
  *   rew,val,done(uint8: 1 = terminated, 2 = truncated/cut -> bootstrap with boot_val)
  *   boot_val [T][n]: V(next obs) where done==2 (ignored elsewhere); last_val [n]: V after T
- *   outputs adv, target_v, disc_ret: [T][n]. */
+ *   outputs adv, target_v, disc_ret: [T][n].
+ *   Reward scaling (use_reward_scaling != 0) divides by `ret_scale`, or by *ret_std_dev + ret_scale when
+ *   ret_std_dev (DEVICE pointer to the running std of the returns, online_mean_std.py:42-48) is not
+ *   NULL -- ret_scale then carries the epsilon; the collector never reads the std back to the host. */
 int pdx_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint8_t* done,
             const float* boot_val, const float* last_val, float gamma, float lam,
-            float ret_scale, int use_reward_scaling,
+            float ret_scale, int use_reward_scaling, const float* ret_std_dev,
             float* adv, float* target_v, float* disc_ret, void* stream);
 /* Column moments of x [rows][dim] (float32, row-major): out[0..dim) += sum x,
  * out[dim..2dim) += sum (x-shift)^2 with shift[dim] (NULL = 0); doubles.  Feeds the

@@ -3,10 +3,19 @@
 #include <cstring>
 #include <cmath>
 #include "pdx_dispatch.cuh"
+#include "pdx_error.h"
 
 namespace {
 
 thread_local char g_err[512] = "";
+}  // namespace
+
+int pdx::set_error(int code, const char* msg) {
+  std::snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+namespace {
 
 int fail(int code, const char* fmt, const char* detail = "") {
   std::snprintf(g_err, sizeof(g_err), fmt, detail);

@@ -37,7 +37,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include "../../include/phoenix_b200.h"
+#include "pdx_error.h"
 
 namespace {
 
@@ -694,13 +696,24 @@ size_t tc_smem_bytes(int k1, int obs_dim, bool x3) {
 
 int tc_select_device_of(const void* ptr) {
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PDX_ERR_NO_DEVICE;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return pdx::set_error(PDX_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+  }
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
     cudaGetLastError();
-    return PDX_ERR_INVALID;
+    return pdx::set_error(PDX_ERR_INVALID, "buffer is not device memory");
   }
-  return cudaSetDevice(attr.device) == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  return cudaSetDevice(attr.device) == cudaSuccess ? PDX_OK : pdx::set_error(PDX_ERR_CUDA, "cudaSetDevice failed");
+}
+
+int tc_status(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return PDX_OK;
+  char msg[256];
+  snprintf(msg, sizeof(msg), "%s: CUDA error: %s", what, cudaGetErrorString(e));
+  return pdx::set_error(PDX_ERR_CUDA, msg);
 }
 
 bool tc_shapes_ok(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
@@ -721,13 +734,15 @@ extern "C" int pdx_policy_tc_timing(long long* out) {
 #endif
 
 extern "C" int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
-  if (!tc_shapes_ok(obs_dim, pi, v, precision)) return PDX_ERR_INVALID;
+  if (!tc_shapes_ok(obs_dim, pi, v, precision))
+    return pdx::set_error(PDX_ERR_INVALID, "tensor-core policy plan: needs two hidden layers <= 64, n_out <= 4, obs_dim <= 64, precision 1 or 3");
   const int k1 = (obs_dim + 7) & ~7;
   return kCommonWords + (precision == 3 ? 2 : 1) * tc_b_words(k1);
 }
 
 extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream) {
-  if (!packed || !tc_shapes_ok(obs_dim, pi, v, precision)) return PDX_ERR_INVALID;
+  if (!packed || !tc_shapes_ok(obs_dim, pi, v, precision))
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_tc_pack: null buffer or shapes outside the tensor-core plan");
   const int rc = tc_select_device_of(packed);
   if (rc) return rc;
   PackArgs p;
@@ -736,7 +751,7 @@ extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMl
   for (int k = 0; k < 3; ++k) { p.pi_w[k] = pi->weight[k]; p.pi_b[k] = pi->bias[k]; p.v_w[k] = v->weight[k]; p.v_b[k] = v->bias[k]; }
   p.out = packed;
   k_pack_tc<<<16, 256, 0, (cudaStream_t)stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  return tc_status("pdx_policy_tc_pack");
 }
 
 extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
@@ -746,7 +761,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   const int32_t overlap = (precision & PDX_POLICY_TC_OVERLAP) ? 1 : 0;
   precision &= ~PDX_POLICY_TC_OVERLAP;
   if (n <= 0 || !obs || !log_std || !packed || !actions || !values || !logp || !tc_shapes_ok(obs_dim, pi, v, precision))
-    return PDX_ERR_INVALID;
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step_tc: null buffer, n <= 0 or shapes outside the tensor-core plan");
   const int rc = tc_select_device_of(obs);
   if (rc) return rc;
   const bool x3 = precision == 3;
@@ -764,7 +779,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   if (smem > set_ref) {
     const cudaError_t e = x3 ? cudaFuncSetAttribute(k_policy_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                              : cudaFuncSetAttribute(k_policy_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return PDX_ERR_CUDA;
+    if (e != cudaSuccess) return tc_status("pdx_policy_step_tc (shared-memory opt-in)");
     set_ref = smem;
   }
   int sms = 148;
@@ -782,6 +797,6 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   static const int pdl = getenv("PDX_PDL") ? atoi(getenv("PDX_PDL")) : 3;     // tuning hook: bit 1 = this kernel
   lc.attrs = attr; lc.numAttrs = (pdl & 2) ? 1 : 0;
   const cudaError_t le = x3 ? cudaLaunchKernelEx(&lc, k_policy_tc<true>, a) : cudaLaunchKernelEx(&lc, k_policy_tc<false>, a);
-  if (le != cudaSuccess) return PDX_ERR_CUDA;
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  if (le != cudaSuccess) { cudaGetLastError(); return pdx::set_error(PDX_ERR_CUDA, cudaGetErrorString(le)); }
+  return tc_status("pdx_policy_step_tc");
 }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include "../../include/phoenix_b200.h"
+#include "pdx_error.h"
 
 namespace {
 
@@ -15,10 +16,12 @@ __global__ void __launch_bounds__(128) k_gae(int64_t T, int64_t n, const float* 
                                              const float* __restrict__ val, const uint8_t* __restrict__ done,
                                              const float* __restrict__ boot_val, const float* __restrict__ last_val,
                                              float gamma, float lam, float ret_scale, int use_scaling,
+                                             const float* __restrict__ ret_std_dev,
                                              float* __restrict__ adv, float* __restrict__ target_v,
                                              float* __restrict__ disc_ret) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (ret_std_dev) ret_scale += ret_std_dev[0];     // running std of the returns, read on the device (no host sync)
   float next_val = last_val[i];       // epoch cut: bootstrap with V(o_T)        (iwpg.py:376-378)
   float next_ret = next_val;          // rews = [..., last_val]                   (core.py:514)
   float next_adv = 0.0f;
@@ -82,36 +85,50 @@ __global__ void k_stats_combine(int world, const double* __restrict__ gathered, 
 }
 
 // The library carries its own static CUDA runtime: select the device the data lives on.
-int select_device_of(const void* ptr) {
+int select_device_of(const void* ptr, int* dev_out = nullptr) {
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PDX_ERR_NO_DEVICE;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return pdx::set_error(PDX_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+  }
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
     cudaGetLastError();
-    return PDX_ERR_INVALID;
+    return pdx::set_error(PDX_ERR_INVALID, "buffer is not device memory");
   }
-  return cudaSetDevice(attr.device) == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  if (dev_out) *dev_out = attr.device;
+  return cudaSetDevice(attr.device) == cudaSuccess ? PDX_OK : pdx::set_error(PDX_ERR_CUDA, "cudaSetDevice failed");
+}
+
+int launch_status(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return PDX_OK;
+  char msg[256];
+  std::snprintf(msg, sizeof(msg), "%s: CUDA error: %s", what, cudaGetErrorString(e));
+  return pdx::set_error(PDX_ERR_CUDA, msg);
 }
 
 }  // namespace
 
 extern "C" int pdx_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint8_t* done,
                        const float* boot_val, const float* last_val, float gamma, float lam,
-                       float ret_scale, int use_reward_scaling, float* adv, float* target_v,
+                       float ret_scale, int use_reward_scaling, const float* ret_std_dev, float* adv, float* target_v,
                        float* disc_ret, void* stream) {
-  if (T <= 0 || n <= 0 || !rew || !val || !done || !boot_val || !last_val || !adv || !target_v || !disc_ret)
-    return PDX_ERR_INVALID;
+  if (T <= 0 || n <= 0) return pdx::set_error(PDX_ERR_INVALID, "pdx_gae: T and n must be positive");
+  if (!rew || !val || !done || !boot_val || !last_val || !adv || !target_v || !disc_ret)
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_gae: null buffer");
   const int rc = select_device_of(rew);
   if (rc) return rc;
   const unsigned grid = (unsigned)((n + 127) / 128);
   k_gae<<<grid, 128, 0, (cudaStream_t)stream>>>(T, n, rew, val, done, boot_val, last_val, gamma, lam,
-                                                ret_scale, use_reward_scaling, adv, target_v, disc_ret);
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+                                                ret_scale, use_reward_scaling, ret_std_dev, adv, target_v, disc_ret);
+  return launch_status("pdx_gae");
 }
 
 extern "C" int pdx_moments(int64_t rows, int32_t dim, const float* x, const double* shift, double* out,
                            void* stream) {
-  if (rows <= 0 || dim <= 0 || dim > 1024 || !x || !out) return PDX_ERR_INVALID;
+  if (rows <= 0 || dim <= 0 || dim > 1024) return pdx::set_error(PDX_ERR_INVALID, "pdx_moments: rows must be positive and dim in [1, 1024]");
+  if (!x || !out) return pdx::set_error(PDX_ERR_INVALID, "pdx_moments: null buffer");
   const int rc = select_device_of(x);
   if (rc) return rc;
   // blockDim = (dim, rows per block): thread (y, x) reads x[row * dim + x], so the linear thread id
@@ -123,15 +140,15 @@ extern "C" int pdx_moments(int64_t rows, int32_t dim, const float* x, const doub
   const unsigned grid = (unsigned)(tiles < 2368 ? tiles : 2368);      // 16 x 148 SMs
   const size_t smem = 2ull * bx * by * sizeof(double);
   k_moments<<<grid, block, smem, (cudaStream_t)stream>>>(rows, dim, x, shift, out);
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  return launch_status("pdx_moments");
 }
 
 extern "C" int pdx_stats_combine(int32_t world, const double* gathered, double* out, void* stream) {
-  if (world <= 0 || !gathered || !out) return PDX_ERR_INVALID;
+  if (world <= 0 || !gathered || !out) return pdx::set_error(PDX_ERR_INVALID, "pdx_stats_combine: bad argument");
   const int rc = select_device_of(gathered);
   if (rc) return rc;
   k_stats_combine<<<1, 32, 0, (cudaStream_t)stream>>>(world, gathered, out);
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  return launch_status("pdx_stats_combine");
 }
 
 // =============================================================================================
@@ -318,19 +335,22 @@ int launch_policy(const PolArgs& a, cudaStream_t st) {
   const size_t words = 2 * ((D + 3) & ~3) + (size_t)(D * HP + HP + HP * HP + HP + HP * 4 + 4) +
                        (size_t)(D * HV + HV + HV * HV + HV + HV * 4 + 4) + (size_t)kHidMax * kPolBlock;
   const size_t smem = words * sizeof(float);
-  if (smem > (size_t)227 * 1024) return PDX_ERR_INVALID;
-  static size_t set = 0;
-  if (smem > set) {
-    if (cudaFuncSetAttribute(k_policy<HP, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PDX_ERR_CUDA;
-    set = smem;
+  if (smem > (size_t)227 * 1024) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: obs_dim too wide for the shared-memory plan");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static size_t set_by_dev[64] = {};                  // opt-in dynamic shared memory is a per-device attribute
+  if (smem > set_by_dev[dev & 63]) {
+    if (cudaFuncSetAttribute(k_policy<HP, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return launch_status("pdx_policy_step (shared-memory opt-in)");
+    set_by_dev[dev & 63] = smem;
   }
   if (a.n == 0) {                                     // pack only
     k_pack_policy<HP, HV><<<8, 256, 0, st>>>(a, const_cast<float*>(a.packed));
-    return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+    return launch_status("pdx_policy_pack");
   }
   const unsigned grid = (unsigned)((a.n + kPolBlock - 1) / kPolBlock);
   k_policy<HP, HV><<<grid, kPolBlock, smem, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? PDX_OK : PDX_ERR_CUDA;
+  return launch_status("pdx_policy_step");
 }
 
 }  // namespace
@@ -340,30 +360,32 @@ static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const f
                            uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
 
 extern "C" int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v) {
-  if (obs_dim <= 0 || !pi || !v) return PDX_ERR_INVALID;
+  if (obs_dim <= 0 || !pi || !v) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_pack_words: bad argument");
   const int64_t D = obs_dim, HP = (pi->hidden[0] <= 52 && pi->hidden[1] <= 52) ? 52 : 64, HV = 64;
   return (D * HP + HP + HP * HP + HP + HP * 4 + 4) + (D * HV + HV + HV * HV + HV + HV * 4 + 4);
 }
 
 extern "C" int pdx_policy_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, float* packed, void* stream) {
-  if (!packed) return PDX_ERR_INVALID;
+  if (!packed) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_pack: null buffer");
   return policy_dispatch(0, obs_dim, packed, nullptr, nullptr, 0.f, pi, v, packed, packed, 0, 0, packed, packed, packed, nullptr, stream);
 }
 
 extern "C" int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                                const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
                                uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
-  if (n <= 0) return PDX_ERR_INVALID;
+  if (n <= 0) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: n must be positive");
   return policy_dispatch(n, obs_dim, obs, mean, std, eps, pi, v, log_std, packed, seed, counter, actions, values, logp, mu_out, stream);
 }
 
 static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                            const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
                            uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
-  if (n < 0 || obs_dim <= 0 || !obs || !pi || !v || !log_std || !packed || !actions || !values || !logp) return PDX_ERR_INVALID;
+  if (n < 0 || obs_dim <= 0 || !obs || !pi || !v || !log_std || !packed || !actions || !values || !logp)
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: null buffer or bad size");
   if (pi->hidden[0] < 1 || pi->hidden[0] > kHidMax || pi->hidden[1] < 1 || pi->hidden[1] > kHidMax || pi->n_out < 1 || pi->n_out > 4)
-    return PDX_ERR_INVALID;
-  if (v->hidden[0] < 1 || v->hidden[0] > kHidMax || v->hidden[1] < 1 || v->hidden[1] > kHidMax || v->n_out != 1) return PDX_ERR_INVALID;
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: actor must have two hidden layers of <= 64 units and <= 4 outputs");
+  if (v->hidden[0] < 1 || v->hidden[0] > kHidMax || v->hidden[1] < 1 || v->hidden[1] > kHidMax || v->n_out != 1)
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: critic must have two hidden layers of <= 64 units and one output");
   const int rc = select_device_of(obs);
   if (rc) return rc;
   PolArgs a;

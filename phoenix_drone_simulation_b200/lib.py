@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 PDX_BUF_STATE_STABLE = 1          # PdxBuffers.flags
 PDX_POLICY_TC_OVERLAP = 0x100     # or-ed into pdx_policy_step_tc's precision
 
@@ -103,7 +103,7 @@ def load():
     lib.pdx_dump_draws.argtypes = [P(PdxConfig), P(PdxBuffers), C.c_void_p, C.c_uint64, C.c_uint64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_gae.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                            C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                            C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_moments.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_policy_step.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, P(PdxMlp), P(PdxMlp),

@@ -33,7 +33,12 @@ class PPO:
                           keep_final_obs=True, **env_kwargs)
         torch.manual_seed(seed)                              # same initial weights on every rank (sync_params)
         self.ac = ActorCritic(self.env.obs_dim, device=self.env.device, dist=dist, seed=seed + 10000 * rank)
-        self.collector = RolloutCollector(self.env, self.ac, steps, gamma=gamma, lam=lam, dist=dist)
+        # The reference resets the env at the start of every roll_out and demands max_ep_len <=
+        # local_steps_per_epoch (iwpg.py:217,353).  With a shorter rollout window that would only ever show
+        # the first `steps` steps of an episode, so episodes then continue across rollouts (the collector
+        # carries obs[T] and bootstraps the cut with V(obs[T]), iwpg.py:376-378).
+        self.collector = RolloutCollector(self.env, self.ac, steps, gamma=gamma, lam=lam, dist=dist,
+                                          reset_each_rollout=steps >= self.env.max_episode_steps)
         self.clip_ratio, self.entropy_coef, self.target_kl = clip_ratio, entropy_coef, target_kl
         self.train_pi_iterations, self.train_v_iterations = train_pi_iterations, train_v_iterations
         self.num_mini_batches, self.use_kl_early_stopping = num_mini_batches, use_kl_early_stopping
@@ -66,7 +71,9 @@ class PPO:
         clip_adv = adv * torch.clamp(ratio, 1 - self.clip_ratio, 1 + self.clip_ratio)
         loss = -torch.min(ratio * adv, clip_adv).mean()
         if self.entropy_coef:
-            loss = loss - self.entropy_coef * (0.5 + 0.5 * math.log(2 * math.pi) + self.ac.log_std).sum()
+            # ppo.py:32: `loss_pi -= entropy_coef * dist.entropy().mean()` -- the mean over the batch AND the
+            # action dimensions of the per-dimension Gaussian entropy
+            loss = loss - self.entropy_coef * (0.5 + 0.5 * math.log(2 * math.pi) + self.ac.log_std).mean()
         return loss, mu, std
 
     def update(self, data):

@@ -51,6 +51,31 @@ def allreduce_episode_stats(stats, dist):
     return stats
 
 
+def gather_episode_stats_async(stats, dist):
+    """Asynchronous form of `allreduce_episode_stats`: starts ONE all-gather of the 8-word vector on the
+    process group's own stream and returns a function that, when called later, makes the current
+    stream wait for it, combines the ranks (pdx_stats_combine) and returns the combined vector.
+    The caller keeps launching env.step kernels in between: the collective overlaps them."""
+    P = _world(dist)
+    if P == 1:
+        return lambda: stats
+    flat = torch.empty(P * 8, dtype=torch.float64, device=stats.device)
+    work = dist.all_gather_into_tensor(flat, stats, async_op=True)
+
+    def finish():
+        work.wait()                                      # stream-level wait, the host does not block
+        gathered = flat.view(P, 8)
+        if stats.is_cuda:
+            st = C.c_void_p(torch.cuda.current_stream(stats.device).cuda_stream)
+            _lib.check(_lib.load().pdx_stats_combine(P, C.c_void_p(gathered.data_ptr()), C.c_void_p(stats.data_ptr()), st))
+        else:
+            stats[:4] = gathered[:, :4].sum(0)
+            stats[4], stats[6] = gathered[:, 4].min(), gathered[:, 6].min()
+            stats[5], stats[7] = gathered[:, 5].max(), gathered[:, 7].max()
+        return stats
+    return finish
+
+
 class EpisodeStats:
     """mean / std / min / max of EpRet and mean of EpLen like EpochLogger.get_stats."""
 
@@ -90,19 +115,25 @@ def column_moments(x, shift=None):
     return out[:dim], out[dim:]
 
 
-class OnlineMeanStd:
+class OnlineMeanStd(torch.nn.Module):
     """Running mean/std with the reference's update rule (online_mean_std.py:70-95):
     n_B = rows * P; the batch mean is the plain average of the per-rank means; the batch second
-    moment is taken about the NEW mean and delta^2 n_A n_B / n_AB is added on top."""
+    moment is taken about the NEW mean and delta^2 n_A n_B / n_AB is added on top.
+
+    Like the reference's (online_mean_std.py:6-16) this is an nn.Module whose mean / std / count are
+    frozen Parameters, so `ActorCritic.state_dict()` carries the normaliser under the reference's key
+    names (`obs_oms.mean`, ...).  Updates are in place: prepared launches hold the tensors' addresses."""
 
     def __init__(self, dim, device, epsilon=1e-5, dist=None, moments_fn=column_moments):
-        self.mean = torch.zeros(dim, dtype=torch.float32, device=device)
-        self.std = torch.ones(dim, dtype=torch.float32, device=device)
-        self.count = torch.zeros(1, dtype=torch.float32, device=device)
+        super().__init__()
+        P = lambda t: torch.nn.Parameter(t, requires_grad=False)
+        self.mean = P(torch.zeros(dim, dtype=torch.float32, device=device))
+        self.std = P(torch.ones(dim, dtype=torch.float32, device=device))
+        self.count = P(torch.zeros(1, dtype=torch.float32, device=device))
         self.eps, self.bound, self.dist = epsilon, 10.0, dist
         self._moments = moments_fn
 
-    def __call__(self, x, subtract_mean=True, clip=False):
+    def forward(self, x, subtract_mean=True, clip=False):
         y = (x - self.mean) / (self.std + self.eps) if subtract_mean else x / (self.std + self.eps)
         return torch.clamp(y, -self.bound, self.bound) if clip else y
 
@@ -113,6 +144,7 @@ class OnlineMeanStd:
             t /= P
         return t
 
+    @torch.no_grad()
     def update(self, x):
         x = x.reshape(-1, self.mean.shape[0])
         rows = x.shape[0]
@@ -133,12 +165,6 @@ class OnlineMeanStd:
         self.count.copy_(n_AB)
         self.std.copy_(torch.sqrt(M2 / n_AB))
 
-    def state_dict(self):
-        return {'mean': self.mean.clone(), 'std': self.std.clone(), 'count': self.count.clone()}
-
-    def load_state_dict(self, sd):
-        self.mean.copy_(sd['mean']); self.std.copy_(sd['std']); self.count.copy_(sd['count'])
-
 
 # ---------------------------------------------------------------------------------------------
 #  GAE
@@ -146,7 +172,8 @@ class OnlineMeanStd:
 def compute_gae(rew, val, done, boot_val, last_val, gamma=0.99, lam=0.95, ret_std=None, eps=1e-5):
     """Buffer.finish_path for a [T, N] lock-step rollout (CUDA kernel pdx_gae).
     done: uint8, 1 = terminated (v=0), 2 = time limit (bootstrap with boot_val[t]).  `ret_std`:
-    running std of the discounted returns -> reward scaling r / (std + eps) clipped to +-10.
+    running std of the discounted returns -> reward scaling r / (std + eps) clipped to +-10; a
+    float, or a one-element float32 CUDA tensor that the kernel reads on the device (no host sync).
     Returns (adv, target_v, discounted_ret), float32 [T, N]."""
     if not rew.is_cuda:
         raise _lib.PhoenixB200Error('compute_gae needs CUDA tensors: there is no CPU fallback')
@@ -157,9 +184,14 @@ def compute_gae(rew, val, done, boot_val, last_val, gamma=0.99, lam=0.95, ret_st
     adv, tv, dr = torch.empty_like(rew), torch.empty_like(rew), torch.empty_like(rew)
     p = lambda t: C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream(rew.device).cuda_stream)
-    scale = float(ret_std) + eps if ret_std is not None else 1.0
+    std_dev = None
+    if torch.is_tensor(ret_std):
+        assert ret_std.is_cuda and ret_std.dtype == torch.float32 and ret_std.numel() == 1
+        std_dev, scale = p(ret_std), eps
+    else:
+        scale = float(ret_std) + eps if ret_std is not None else 1.0
     _lib.check(_lib.load().pdx_gae(T, n, p(rew), p(val), p(done), p(boot_val), p(last_val), gamma, lam,
-                                   scale, 1 if ret_std is not None else 0, p(adv), p(tv), p(dr), st))
+                                   scale, 1 if ret_std is not None else 0, std_dev, p(adv), p(tv), p(dr), st))
     return adv, tv, dr
 
 
@@ -173,6 +205,27 @@ def _mlp(sizes, act):
         torch.nn.init.kaiming_uniform_(lin.weight, a=math.sqrt(5))          # core.py:34-35
         layers += [lin, act() if j < len(sizes) - 2 else torch.nn.Identity()]
     return torch.nn.Sequential(*layers)
+
+
+class _Net(torch.nn.Module):
+    """MLP held under `.net` like the reference's MLPGaussianActor / MLPCritic (core.py:227-310), so
+    that state_dict keys read `pi.net.0.weight`, `v.net.4.bias`, ... as in a reference checkpoint."""
+
+    def __init__(self, sizes, act):
+        super().__init__()
+        self.net = _mlp(sizes, act)
+
+    def forward(self, obs):
+        return self.net(obs)
+
+    def __iter__(self):
+        return iter(self.net)
+
+
+class _Actor(_Net):
+    def __init__(self, sizes, act):
+        super().__init__(sizes, act)
+        self.log_std = torch.nn.Parameter(torch.full((sizes[-1],), math.log(0.5)), requires_grad=False)   # core.py:238-240
 
 
 class ActorCritic(torch.nn.Module):
@@ -189,18 +242,40 @@ class ActorCritic(torch.nn.Module):
         self.fused = (fused and len(pi_hidden) == 2 and len(v_hidden) == 2 and max(*pi_hidden, *v_hidden) <= 64
                       and act_dim <= 4)
         self.seed, self._counter = int(seed), 0
-        self.pi = _mlp([obs_dim, *pi_hidden, act_dim], torch.nn.ReLU)
-        self.v = _mlp([obs_dim, *v_hidden, 1], torch.nn.Tanh)
-        self.log_std = torch.nn.Parameter(torch.full((act_dim,), math.log(0.5)), requires_grad=False)
+        self.pi = _Actor([obs_dim, *pi_hidden, act_dim], torch.nn.ReLU)
+        self.v = _Net([obs_dim, *v_hidden, 1], torch.nn.Tanh)
         self.to(device)
         self.obs_oms = OnlineMeanStd(obs_dim, device, dist=dist) if use_standardized_obs else None
         self.ret_oms = OnlineMeanStd(1, device, dist=dist) if use_scaled_rewards else None
 
+    @property
+    def log_std(self):
+        return self.pi.log_std
+
     def set_log_std(self, frac):                                              # core.py:268-276
-        self.log_std.fill_(math.log(0.499 * frac + 0.01))
+        self.pi.log_std.fill_(math.log(0.499 * frac + 0.01))
+
+    # the Philox position of the policy noise is part of a checkpoint (a restored run must not replay draws)
+    def get_extra_state(self):
+        return {'seed': self.seed, 'counter': self._counter}
+
+    def set_extra_state(self, state):
+        self.seed, self._counter = int(state['seed']), int(state['counter'])
 
     @torch.no_grad()
     def value(self, obs):
+        """V(obs) [N].  On CUDA with kernel-supported shapes this is the fused policy kernel (its action
+        draw is discarded and does not advance the policy's Philox counter); otherwise the torch modules."""
+        if self.fused and obs.is_cuda and obs.dtype == torch.float32 and obs.dim() == 2 and self.log_std.shape[0] == 4:
+            n = obs.shape[0]
+            scratch = getattr(self, '_value_scratch', None)
+            if scratch is None or scratch[0].shape[0] != n or scratch[0].device != obs.device:
+                scratch = (torch.empty((n, 4), dtype=torch.float32, device=obs.device),
+                           torch.empty(n, dtype=torch.float32, device=obs.device))
+                self._value_scratch = scratch
+            val = torch.empty(n, dtype=torch.float32, device=obs.device)
+            self._launch_into(obs.contiguous(), scratch[0], val, scratch[1], None, counter=0)
+            return val
         o = obs.float()
         if self.obs_oms:
             o = self.obs_oms(o)
@@ -253,15 +328,19 @@ class ActorCritic(torch.nn.Module):
         for t in (act, val, logp):
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
         assert act.shape == (n, 4)
-        pi, v = self._mlp_struct(self.pi, self.log_std.shape[0]), self._mlp_struct(self.v, 1)
         self._counter += 1
+        self._launch_into(obs, act, val, logp, mu, self._counter)
+
+    def _launch_into(self, obs, act, val, logp, mu, counter):
+        n, d = obs.shape
+        pi, v = self._mlp_struct(self.pi, self.log_std.shape[0]), self._mlp_struct(self.v, 1)
         oms = self.obs_oms
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         st = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         pack = self._packed_weights(d, pi, v, st)
         head = (n, d, p(obs), p(oms.mean) if oms else None, p(oms.std) if oms else None, oms.eps if oms else 0.0,
                 C.byref(pi), C.byref(v), p(self.log_std.data), p(pack), self.seed)
-        _lib.check(self._launch_policy(head, self._counter, (p(act), p(val), p(logp), p(mu)), st))
+        _lib.check(self._launch_policy(head, counter, (p(act), p(val), p(logp), p(mu)), st))
 
     def prepare_step_into(self, obs, act, val, logp, overlap=False):
         """Handle for `step_prepared`: all ctypes arguments of one fused policy step, built once.
@@ -292,7 +371,9 @@ class ActorCritic(torch.nn.Module):
 
     @torch.no_grad()
     def step(self, obs, generator=None):
-        """obs [N, D] on device -> (action [N, 4], value [N], logp [N]), all on device."""
+        """obs [N, D] on device -> (action [N, 4], value [N], logp [N]), all on device.  CUDA float32
+        observations with kernel-supported shapes always take the fused kernel; the torch expression
+        below serves CPU tensors (host-logic tests), explicit generators and wider networks."""
         if self.fused and obs.is_cuda and generator is None and obs.dtype == torch.float32 and self.log_std.shape[0] == 4:
             n = obs.shape[0]
             act = torch.empty((n, 4), dtype=torch.float32, device=obs.device)
@@ -420,7 +501,7 @@ class RolloutCollector:
         done = torch.where(self.trunc > 0, torch.full_like(self.term, 2), self.term)
         ret_std = ac.ret_oms.std if ac.ret_oms is not None else None
         adv, target_v, disc_ret = compute_gae(self.rew, self.val, done, self.boot, last_val, self.gamma,
-                                              self.lam, ret_std.item() if ret_std is not None else None)
+                                              self.lam, ret_std.data if ret_std is not None else None)
         stats = allreduce_episode_stats(env.episode_stats(), self.dist)
         torch.cuda.nvtx.range_pop()
         return {'obs': self.obs[:T], 'act': self.act, 'adv': adv, 'target_v': target_v, 'log_p': self.logp,

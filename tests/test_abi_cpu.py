@@ -131,7 +131,7 @@ def test_no_cpu_fallback(lib):
         setattr(b, f, host.ctypes.data)
     assert lib.pdx_step(C.byref(c), C.byref(b), host.ctypes.data, 0, 1, None) == -3     # PDX_ERR_NO_DEVICE
     assert b'no CPU path' in lib.pdx_last_error()
-    assert lib.pdx_gae(4, 4, *([host.ctypes.data] * 5), 0.99, 0.95, 1.0, 0, *([host.ctypes.data] * 3), None) == -3
+    assert lib.pdx_gae(4, 4, *([host.ctypes.data] * 5), 0.99, 0.95, 1.0, 0, None, *([host.ctypes.data] * 3), None) == -3
 
 
 def test_product_package_does_not_import_oracle():

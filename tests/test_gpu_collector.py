@@ -300,3 +300,81 @@ def test_simopt_objective_recovers_motor_parameters():
     best = cands[int(loss.argmin())]
     assert best[0] == true_t2w, (best, loss)
     assert np.isfinite(loss).all() and loss.min() < 0.5 * np.median(loss)
+
+
+def test_stats_combine_kernel():
+    """pdx_stats_combine (utils/mpi_tools.py:217-240 across ranks): sums of words 0..3, minima of 4 and 6,
+    maxima of 5 and 7 over the gathered per-rank vectors."""
+    import ctypes as C
+    from phoenix_drone_simulation_b200 import lib as _lib
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 8):
+        g = rng.normal(0, 50, (world, 8))
+        g[:, 0] = rng.integers(0, 100, world)
+        gathered = torch.as_tensor(g, device='cuda').contiguous()
+        out = torch.zeros(8, dtype=torch.float64, device='cuda')
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().pdx_stats_combine(world, C.c_void_p(gathered.data_ptr()), C.c_void_p(out.data_ptr()), st))
+        ref = np.concatenate([g[:, :4].sum(0), [g[:, 4].min(), g[:, 5].max(), g[:, 6].min(), g[:, 7].max()]])
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-14, atol=1e-12)
+
+
+def _nccl_worker(rank, world, port, batches, ep, out_q):
+    import torch.distributed as dist
+    from phoenix_drone_simulation_b200.rollout import (OnlineMeanStd, allreduce_episode_stats, gather_episode_stats_async,
+                                                       EpisodeStats)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world, device_id=dev)
+    dim = batches[0][0].shape[1]
+    oms = OnlineMeanStd(dim, dev, dist=dist)                      # CUDA moments kernel + NCCL all-reduces
+    for b in batches:
+        oms.update(torch.as_tensor(b[rank], device=dev))
+    x = np.asarray(ep[rank], np.float64)
+    vec = [len(x), x.sum(), (x ** 2).sum(), 3.0 * len(x), x.min(), x.max(), 7.0 + rank, 100.0 + rank]
+    stats = torch.tensor(vec, dtype=torch.float64, device=dev)
+    allreduce_episode_stats(stats, dist)                          # all-gather + pdx_stats_combine
+    later = gather_episode_stats_async(torch.tensor(vec, dtype=torch.float64, device=dev), dist)
+    torch.zeros(1 << 20, device=dev).add_(1)                      # unrelated work between start and finish
+    stats2 = later()
+    es = EpisodeStats(stats)
+    out_q.put((rank, oms.mean.cpu().numpy(), oms.std.cpu().numpy(), float(oms.count), es.as_dict(), es.len_min, es.len_max,
+               stats2.cpu().numpy(), stats.cpu().numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_nccl_world2_running_stats_and_episode_stats():
+    """The NCCL branch of OnlineMeanStd._avg and pdx_stats_combine behind one NCCL all-gather, world size 2,
+    against the oracle -- the same expectations as the gloo test of tests/test_collector_oracle.py."""
+    import socket
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(0)
+    world, dim = 2, 6
+    batches = [[rng.normal(b, 1 + b, (32, dim)).astype(np.float32) for _ in range(world)] for b in range(3)]
+    ep = [rng.normal(-50, 20, 11).astype(np.float32), rng.normal(-80, 5, 5).astype(np.float32)]
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, batches, ep, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    o = co.OnlineMeanStdOracle(dim)
+    for b in batches:
+        o.update(b)
+    mean, std, mn, mx = co.statistics_scalar(ep)
+    for _, m, s_, c, d, lmin, lmax, async_stats, sync_stats in res:
+        np.testing.assert_allclose(m, o.mean, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(s_, o.std, rtol=2e-5, atol=1e-6)
+        assert c == float(o.count[0]) == 3 * 32 * world
+        assert d['Episodes'] == 16
+        assert abs(d['EpRet/Mean'] - mean) < 1e-3 and abs(d['EpRet/Std'] - std) < 1e-2
+        assert abs(d['EpRet/Min'] - mn) < 1e-4 and abs(d['EpRet/Max'] - mx) < 1e-4
+        assert (lmin, lmax) == (7.0, 101.0)
+        np.testing.assert_array_equal(async_stats, sync_stats)      # asynchronous form == synchronous form
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
