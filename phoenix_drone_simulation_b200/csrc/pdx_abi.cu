@@ -119,7 +119,7 @@ int pdx_config_finalize(PdxConfig* cfg) {
 int pdx_state_quads(const PdxConfig* cfg) {
   if (validate(cfg)) return PDX_ERR_INVALID;
   const pdx::Layout L = layout_of(cfg);
-  return L.n_quads + (cfg->history - 1) * L.hist_quads;
+  return L.n_quads + (cfg->history - 1) * L.hist_quads + pdx::kPackSlots * L.pack_quads;
 }
 
 int pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int* n_words) {
@@ -132,7 +132,8 @@ int pdx_state_field(const PdxConfig* cfg, const char* name, int* first_word, int
       {"inertia", L.inertia, 3}, {"ftf1", L.ftf1, 1}, {"motor_b", L.motor_b, 4},
       {"motor_k", L.motor_k, 4}, {"motor_x", L.motor_x, 4}, {"ring", L.ring, 8},
       {"ring_idx", L.ring_idx, 1}, {"ou", L.ou, 4}, {"last_action", L.last_action, 4}, {"pid", L.pid, 12},
-      {"ep_return", L.ep_return, 1}, {"ep_length", L.ep_length, 1},
+      {"ep_return", L.ep_return, 1}, {"ep_length", L.ep_length, 1}, {"ep_index", L.ep_index, 1},
+      {"pool", (L.n_quads + (cfg->history - 1) * L.hist_quads) * 4, pdx::kPackSlots * L.pack_quads * 4},
       {"ref_offset", L.ref_offset, 1}, {"gyro_bias", L.gyro_bias, 3}, {"gyro_lpf", L.gyro_lpf, 3},
       {"hist", L.n_quads * 4, (cfg->history - 1) * L.hist_quads * 4},
   };
@@ -164,8 +165,10 @@ int64_t pdx_rollout_bytes(const PdxConfig* cfg, int32_t n_steps) {
   const int64_t sz = cfg->dtype == PDX_DTYPE_F32 ? 4 : 8;
   const int64_t E = L.core_dim + 4, H = cfg->history;
   // per launch: state + history read once and written once; per step: action in, observation
-  // row, reward, cost and the two flag bytes out.
-  const int64_t once = (L.n_words + (H - 1) * E) * sz + (L.n_words + (H - 1) * E) * sz;
+  // row, reward, cost and the two flag bytes out.  The bookkeeping word of the reset-package pool
+  // (ep_index) and the pool itself are this implementation's, not the algorithm's: not counted.
+  const int64_t words = L.n_words - 1;
+  const int64_t once = (words + (H - 1) * E) * sz + (words + (H - 1) * E) * sz;
   const int64_t per_step = (H * E + 2) * sz + 16 + 2;
   return once + per_step * n_steps;
 }

@@ -61,11 +61,13 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
 
 // Launch shape of k_rollout: threads per block (<= 128 so that a 65,536-env shard still spreads
 // over all 148 SMs) and one or two observation tiles, chosen to maximise the warps resident per SM
-// under the shared-memory plan (the kernel is capped at 128 registers: 16 warps per SM at most);
+// under the shared-memory plan.  The kernel is compiled for 144 registers (no spills on the step path):
+// 64-thread blocks then fit 7 per SM = 14 warps, which is what a 65,536-env shard offers per SM
+// (13.8) -- warps of a block share nothing but the launch, so small blocks cost nothing;
 // ties go to double buffering, then to the larger block.
 struct LaunchShape { int block, tiles; size_t smem; };
 template <class T>
-static LaunchShape pick_shape(int D) {
+static LaunchShape pick_shape(int D, int E) {
   int forced = 0;
   if (const char* e = getenv("PDX_BLOCK")) {          // tuning hook: 32 / 64 / 128 / 256
     const int b = atoi(e);
@@ -77,7 +79,7 @@ static LaunchShape pick_shape(int D) {
   for (int bi = 0; bi < 3; ++bi) {
     const int block = forced ? forced : blocks[bi];
     for (int tiles = 2; tiles >= 1; --tiles) {
-      const size_t smem = rollout_smem_bytes<T>(block, D, tiles);
+      const size_t smem = rollout_smem_bytes<T>(block, D, tiles, E);
       if (smem > (size_t)227 * 1024) continue;
       const int by_smem = (int)(((size_t)228 * 1024) / (smem + 1024));
       const int by_regs = 65536 / (128 * block);
@@ -99,19 +101,20 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     else k_reset<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, 0, st>>>(ka);
     return cudaGetLastError();
   }
-  const LaunchShape shape = pick_shape<T>(ka.c.obs_dim);
+  const LaunchShape shape = pick_shape<T>(ka.c.obs_dim, ka.c.core_dim + 4);
   if (shape.block == 0) return cudaErrorInvalidConfiguration;
   const int block = shape.block;
   const size_t smem = shape.smem;
   KArgs<T> kb = ka;
   kb.n_tiles = shape.tiles;
-  static size_t smem_set[16] = {0};                 // per device: opt-in dynamic shared memory
+  const bool wide = (ka.c.obs_dim & 15) == 0;
+  auto kern = wide ? k_rollout<T, TASK, PHYS, NOISE, RNG, PID, true> : k_rollout<T, TASK, PHYS, NOISE, RNG, PID, false>;
+  static size_t smem_set[2][16] = {};               // per variant and device: opt-in dynamic shared memory
   const int dev = ka.b.device & 15;
-  if (smem > smem_set[dev]) {
-    const cudaError_t e = cudaFuncSetAttribute(k_rollout<T, TASK, PHYS, NOISE, RNG, PID>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > smem_set[wide][dev]) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    smem_set[dev] = smem;
+    smem_set[wide][dev] = smem;
   }
   const unsigned grid = (unsigned)((n + block - 1) / block);
   // programmatic stream serialisation: the grid may start while its predecessor drains; the kernel
@@ -125,7 +128,7 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
   // opt-in per call (PDX_BUF_STATE_STABLE): measured, early launch of this kernel AND of a one-CTA-per-SM
   // tensor-core policy kernel around it collapses throughput (profiles/r1_summary.md), so the caller decides
   lc.attrs = attr; lc.numAttrs = ((pdl & 1) && (ka.b.flags & PDX_BUF_STATE_STABLE)) ? 1 : 0;
-  return cudaLaunchKernelEx(&lc, k_rollout<T, TASK, PHYS, NOISE, RNG, PID>, kb);
+  return cudaLaunchKernelEx(&lc, kern, kb);
 }
 
 template <class T, int TASK, int PHYS, bool PID>

@@ -16,6 +16,10 @@
 #pragma once
 #include "pdx_model.cuh"
 
+#ifndef PDX_FLUSH_INLINE
+#define PDX_FLUSH_INLINE __forceinline__
+#endif
+
 namespace pdx {
 
 constexpr int kMaxBlock = 512;     // threads per block are chosen at run time (<= kMaxBlock)
@@ -34,14 +38,16 @@ struct KArgs {
   int n_tiles;      // 2: observation tiles double buffered; 1: one tile, shifted in place
 };
 
+// `package`: the draws of in-kernel auto-reset number `counter` of this environment (a stream of its
+// own: an explicit pdx_reset at call counter c and auto-reset package c must not share draws)
 template <class T, int RNG>
 __device__ __forceinline__ Rng<T, RNG> make_rng(const KArgs<T>& a, uint64_t counter, int64_t i,
-                                                const double* tape, double* dump) {
+                                                const double* tape, double* dump, bool package = false) {
   Rng<T, RNG> r;
   const uint64_t env = (uint64_t)(a.b.env_offset + i);
   r.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   r.env_lo = (uint32_t)env;
-  r.env_hi = (uint32_t)(env >> 32) ^ ((uint32_t)(counter >> 32) << 8);
+  r.env_hi = (uint32_t)(env >> 32) ^ ((uint32_t)(counter >> 32) << 8) ^ (package ? 0x80000000u : 0u);
   r.ctr_lo = (uint32_t)counter;
   r.tape = tape ? tape + i : nullptr;
   r.stride = a.b.n_envs;
@@ -242,17 +248,31 @@ __device__ __forceinline__ void store_history(T* state, int64_t n, int64_t i, in
 }
 
 // ---------------------------------------------------------------------------------------------
-//  constructor: zero state, nominal parameters, base.py:143's compute_observation()
+//  Pre-computed reset packages (production Philox path).
+//
+//  An env.reset() is as long as an env.step (two noisy observation calls, ~20 Philox calls, three
+//  Euler->quaternion conversions), and with U(-1,1) actions 11 % of the environments finish per step:
+//  3.6 of a warp's 32 lanes.  Running the reset where it happens executes all of it at 11 % lane
+//  occupancy, every step.  Nothing in a reset depends on the episode that just ended except three
+//  carried words (gyro bias, the stale body rates that seed the low pass: quirks A.6-5 / A.6-8) and
+//  those enter LINEARLY.  So the reset of episode p of environment j is keyed by (seed, j, p) -- not
+//  by the step at which it happens -- and computed ahead of time:
+//    * every environment owns kPackSlots package slots behind its history slots in `state`; slot p & 3 holds
+//      the complete state of a freshly reset environment plus its two reset observations, computed
+//      with zero carried words (reset_env below, unchanged);
+//    * a lane whose episode ends LOADS its package (divergent, but ~16 128-bit loads and a dozen
+//      FMAs for the carried words instead of ~500 instructions) and marks the slot pending;
+//    * when a warp has 32 pending slots, its 32 lanes regenerate them together, one package per lane,
+//      fully converged.  The pending bits live in the state, so when that happens depends only on the
+//      history of the 32 environments, not on how the steps are split over launches.
+//  The tape (parity) instantiation keeps the in-thread reset; in dump mode it draws with the same
+//  (seed, j, p) keys, so pdx_dump_draws reports exactly the draws a package was built from.
 // ---------------------------------------------------------------------------------------------
 template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
-__global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
+__device__ __forceinline__ void init_nominal(Model<T, TASK, PHYS, NOISE, RNG, PID>& m) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
-  const int64_t n = a.b.n_envs;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Mo m(a.c);
-  const DevCfg<T>& c = a.c;
+  const DevCfg<T>& c = m.c;
 #pragma unroll
   for (int k = 0; k < Mo::NW; ++k) m.w[k] = T(0);
   m.w[L.xyz + 2] = T(1);                                  // agents.py:32
@@ -269,6 +289,164 @@ __global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
       m.w[L.motor_k + k] = c.max_thrust;                      // agents.py:200
     }
   }
+}
+
+// first plane of the package pool in the state tensor.  The pool region holds kPackSlots * pack_quads planes
+// worth of memory but is laid out per package: quad q of the package in slot s of environment j sits at
+//   state + ((pool_plane * n + (s * n + j) * pack_quads + q) * 4 reals
+// i.e. one package is pack_quads * 16 contiguous bytes (two or three cache lines: a finished lane
+// fetches it with a few 128-bit loads of the same lines, and can prefetch it).
+template <class Mo>
+__device__ __forceinline__ int pool_plane(int history) {
+  return Mo::L.n_quads + (history - 1) * Mo::QH;
+}
+template <class Mo, class T>
+__device__ __forceinline__ T* package_ptr(T* state, int64_t n, int64_t j, int history, int slot) {
+  return state + (((int64_t)pool_plane<Mo>(history) * n + ((int64_t)slot * n + j) * Mo::L.pack_quads) << 2);
+}
+template <class T> __device__ __forceinline__ void load_quad_at(const T* p, int q, T* out) { load_quad(p, (int64_t)0, (int64_t)q, 0, out); }
+template <class T> __device__ __forceinline__ void store_quad_at(T* p, int q, const T* in) { store_quad(p, (int64_t)0, (int64_t)q, 0, in); }
+
+// package p of environment j (local index) -> its slot.  Zero carried words: the consumer adds their
+// (linear) contribution.
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
+__device__ __forceinline__ void gen_package(const KArgs<T>& a, int64_t j, uint32_t p) {
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
+  constexpr Layout L = Mo::L;
+  constexpr int C = Mo::C;
+  Mo g(a.c);
+  init_nominal(g);
+  const Rng<T, RNG> rng = make_rng<T, RNG>(a, (uint64_t)p, j, nullptr, nullptr, true);
+  const T stale[3] = {T(0), T(0), T(0)};
+  T o1[C], o2[C];
+  reset_env(g, rng, stale, o1, o2);
+  T* pk = package_ptr<Mo>(reinterpret_cast<T*>(a.b.state), a.b.n_envs, j, a.c.history, (int)(p & (uint32_t)(kPackSlots - 1)));
+#pragma unroll
+  for (int q = 0; q < L.n_quads; ++q) store_quad_at(pk, q, &g.w[4 * q]);
+#pragma unroll
+  for (int q = 0; q < (2 * C + 3) / 4; ++q) {
+    T v[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = 4 * q + l;
+      v[l] = idx < C ? o1[idx < C ? idx : 0] : idx < 2 * C ? o2[idx < 2 * C && idx >= C ? idx - C : 0] : T(0);
+    }
+    store_quad_at(pk, L.n_quads + q, v);
+  }
+}
+
+// Regenerates pending packages of the 32 environments of a warp, one package per lane and pass (called by
+// all 32 lanes together; `e_mine` / `pend` are the caller lane's episode index and pending bits, the new
+// pending bits are returned).  Work items of a pass: the packages some lane needs NEXT first, then the
+// other pending slot-0 packages in lane order, slot 1, ...  One pass; more only if more than 32 lanes
+// were waiting for their next package (impossible: one per lane).
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
+__device__ __forceinline__ int flush_pending(const KArgs<T>& a, int64_t warp_base, int e_mine, int pend) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int next = (e_mine + 1) & (kPackSlots - 1);
+  // group 0: the next-needed slot of each lane where that slot is pending; groups 1..kPackSlots: slot s - 1
+  // of each lane where pending and not already in group 0
+  unsigned b[kPackSlots + 1];
+  int start[kPackSlots + 2];
+  b[0] = __ballot_sync(full, (pend >> next) & 1);
+  start[0] = 0;
+  start[1] = __popc(b[0]);
+#pragma unroll
+  for (int s = 0; s < kPackSlots; ++s) {
+    b[s + 1] = __ballot_sync(full, ((pend >> s) & 1) && s != next);
+    start[s + 2] = start[s + 1] + __popc(b[s + 1]);
+  }
+  const int total = start[kPackSlots + 1];
+  int grp = -1, src = 0;
+  const bool has = lane < total;
+#pragma unroll
+  for (int g = 0; g <= kPackSlots; ++g)
+    if (has && lane >= start[g] && lane < start[g + 1]) { grp = g; src = (int)__fns(b[g], 0, lane - start[g] + 1); }
+  const int e_src = __shfl_sync(full, e_mine, src);
+  if (has) {
+    const int slot = grp == 0 ? ((e_src + 1) & (kPackSlots - 1)) : grp - 1;
+    // slot s holds a package p > e with p = s (mod kPackSlots): the first one the owner will ask this slot for
+    const int p = e_src + 1 + ((slot - (e_src + 1)) & (kPackSlots - 1));
+    gen_package<T, TASK, PHYS, NOISE, RNG, PID>(a, warp_base + src, (uint32_t)p);
+  }
+  // which of my pending packages were among the first 32 items
+  if (((pend >> next) & 1) && __popc(b[0] & ((1u << lane) - 1u)) < 32) pend &= ~(1 << next);
+#pragma unroll
+  for (int s = 0; s < kPackSlots; ++s)
+    if (((pend >> s) & 1) && s != next && start[s + 1] + __popc(b[s + 1] & ((1u << lane) - 1u)) < 32) pend &= ~(1 << s);
+  __syncwarp();                                            // package stores -> visible to the lanes that load them
+  return pend;
+}
+
+// A finished environment takes its next package: everything a reset writes comes from the package,
+// the words a reset keeps (OU state, gyro bias, episode counters of the pool) stay, and the carried
+// words enter the gyro chain of the two reset observations linearly:
+//   b1 = pi b0 + s n1            lp1 = (1-r) stale + r (om + b1 + W n1')
+//   b2 = pi b1 + s n2            lp2 = (1-r) lp1   + r (om + b2 + W n2')
+// (sensors.py:121-134, envs/utils.py:76-79; the package holds the b0 = stale = 0 solution).
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
+__device__ __forceinline__ void take_package(Model<T, TASK, PHYS, NOISE, RNG, PID>& m, T* state, int64_t n, int64_t i,
+                                             int history, const T stale[3], T* o1, T* o2) {
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
+  constexpr Layout L = Mo::L;
+  constexpr int C = Mo::C;
+  const DevCfg<T>& c = m.c;
+  T* w = m.w;
+  const int ew = (int)w[L.ep_index];                 // 16 e + pending bits
+  const int e = ew >> 4;
+  const int slot = (e + 1) & (kPackSlots - 1);
+  const T* pk = package_ptr<Mo>(state, n, i, history, slot);
+  T ou[4], b0[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ou[k] = w[L.ou + k];
+  if constexpr (NOISE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b0[k] = w[L.gyro_bias + k];
+  }
+#pragma unroll
+  for (int q = 0; q < L.n_quads; ++q) load_quad_at(pk, q, &w[4 * q]);
+#pragma unroll
+  for (int q = 0; q < (2 * C + 3) / 4; ++q) {
+    T v[4];
+    load_quad_at(pk, L.n_quads + q, v);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = 4 * q + l;
+      if (idx < C) o1[idx < C ? idx : 0] = v[l];
+      else if (idx < 2 * C) o2[idx < 2 * C && idx >= C ? idx - C : 0] = v[l];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[L.ou + k] = ou[k];
+  if constexpr (NOISE) {
+    const T r = c.lpf_ratio, pi1 = c.gyro_pi, pi2 = c.gyro_pi * c.gyro_pi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T d1 = (T(1) - r) * stale[k] + r * (pi1 * b0[k]);          // lp1 - lp1'
+      const T d2 = (T(1) - r) * d1 + r * (pi2 * b0[k]);                // lp2 - lp2'
+      o1[10 + k] += d1;
+      o2[10 + k] += d2;
+      w[L.gyro_lpf + k] += d2;
+      w[L.gyro_bias + k] += pi2 * b0[k];
+    }
+  }
+  w[L.ep_index] = (T)((ew + 16) | (1 << slot));
+}
+
+// ---------------------------------------------------------------------------------------------
+//  constructor: zero state, nominal parameters, base.py:143's compute_observation()
+// ---------------------------------------------------------------------------------------------
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
+__global__ void __launch_bounds__(kMaxBlock) k_init(const __grid_constant__ KArgs<T> a) {
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
+  constexpr Layout L = Mo::L;
+  const int64_t n = a.b.n_envs;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Mo m(a.c);
+  const DevCfg<T>& c = a.c;
+  init_nominal(m);
   if constexpr (NOISE) {
     const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter, i, a.b.tape_init, a.dump_init);
     T z[3];
@@ -280,6 +458,12 @@ __global__ void __launch_bounds__(kMaxBlock) k_init(const KArgs<T> a) {
   m.store(state, n, i, true);
   const T zero[4] = {T(0), T(0), T(0), T(0)};
   for (int qd = 0; qd < (c.history - 1) * Mo::QH; ++qd) store_quad(state, n, i, L.n_quads + qd, zero);
+  if constexpr (RNG == PDX_RNG_PHILOX) {                   // the first two reset packages of every environment
+#pragma unroll 1
+    for (uint32_t p = 1; p <= (uint32_t)kPackSlots; ++p) gen_package<T, TASK, PHYS, NOISE, RNG, PID>(a, i, p);
+  } else {
+    for (int qd = 0; qd < kPackSlots * L.pack_quads; ++qd) store_quad(state, n, i, pool_plane<Mo>(c.history) + qd, zero);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -353,57 +537,60 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Shared-memory plan of k_rollout (dynamic shared memory):
-//   T tile0, tile1 [B][D]                     observation rows of the block, layout == global slice
-//                                             (tile1 only when n_tiles == 2)
-//   T rtab [B/32][kResetRows*4][kResetChunk]  per warp: reset draws of up to kResetChunk finished envs
-//   double acc_sum [4][B], T acc_ext [4][B]   per-thread episode statistics (n, sum ret, sum ret^2,
-//                                             sum len; min/max ret, min/max len), reduced once
-//   int tile_free                             last step whose bulk copy is known to have left its tile
-//   unsigned char fin_lane [B]                per warp: lanes that finished this step, in lane order
+// Shared-memory plan of k_rollout (dynamic shared memory), B threads = W warps:
+//   T tile0, tile1 [B][D]        observation rows; warp w owns rows [32 w, 32 w + 32) of each tile, which
+//                                have exactly the layout of its slice of the row-major [n_envs][D]
+//                                output (tile1 only when n_tiles == 2)
+//   T stage [W][E][32]           only when D is a multiple of 16: column-major staging of the new entry
+//   T acc_ext [4][B], double acc_sum [4][B]   per-thread episode statistics (min/max ret, min/max len;
+//                                n, sum ret, sum ret^2, sum len), reduced once per launch
 template <class T>
-__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_tiles) {
-  size_t bytes = ((size_t)n_tiles * block * D + (size_t)(block / 32) * kResetRows * 4 * kResetChunk + (size_t)4 * block) * sizeof(T);
-  bytes = (bytes + 15) & ~(size_t)15;
-  return bytes + sizeof(double) * 4 * block + 16 + kMaxBlock;
+__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_tiles, int E) {
+  size_t words = (size_t)n_tiles * block * D + (size_t)4 * block;
+  if ((D & 15) == 0) words += (size_t)(block / 32) * E * 32;
+  size_t bytes = (words * sizeof(T) + 15) & ~(size_t)15;
+  return bytes + sizeof(double) * 4 * block;
 }
 
 // ---------------------------------------------------------------------------------------------
 //  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID>
-__global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
+// WIDE: obs_dim is a multiple of 16 (rows walked in rotated order, see below) -- a template parameter
+// because as a run-time branch it made ptxas spill the 17 words of the new entry on BOTH paths.
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE>
+__global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
+  constexpr bool POOL = RNG == PDX_RNG_PHILOX;       // pre-computed reset packages (see gen_package)
   const DevCfg<T>& c = a.c;
   const int64_t n = a.b.n_envs;
   const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t block_base = (int64_t)blockIdx.x * B;
   const int64_t i = block_base + tid;
   const bool valid = i < n;
-  const int rows = (int)min((int64_t)B, n - block_base);
   const int D = c.obs_dim, H = c.history;
+  const unsigned full = 0xffffffffu;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile0 = reinterpret_cast<T*>(smem_raw);
   const int NT = a.n_tiles;
   T* tile1 = NT == 2 ? tile0 + (size_t)B * D : tile0;
-  T* rtab = tile0 + (size_t)NT * B * D + (size_t)warp * (kResetRows * 4 * kResetChunk);
-  T* acc_ext = tile0 + (size_t)NT * B * D + (size_t)(B >> 5) * (kResetRows * 4 * kResetChunk);
-  const size_t off = (((size_t)NT * B * D + (size_t)(B >> 5) * kResetRows * 4 * kResetChunk + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
+  constexpr bool wide = WIDE;
+  T* stg = tile0 + (size_t)NT * B * D + (size_t)warp * (E * 32);          // valid only when `wide`
+  const size_t words_before_acc = (size_t)NT * B * D + (wide ? (size_t)(B >> 5) * E * 32 : 0);
+  T* acc_ext = tile0 + words_before_acc;
+  const size_t off = ((words_before_acc + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
   double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
-  int* s_tile_free = reinterpret_cast<int*>(smem_raw + off + sizeof(double) * 4 * B);   // accessed with atomics only
-  unsigned char* s_fin_lane = smem_raw + off + sizeof(double) * 4 * B + 16 + (warp << 5);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     acc_sum[k * B + tid] = 0.0;
     acc_ext[k * B + tid] = (k & 1) ? T(-1e30) : T(1e30);
   }
-  if (tid == 0) *s_tile_free = -1;
-  __syncthreads();
 
   Mo m(c);
+#pragma unroll
+  for (int k = 0; k < Mo::NW; ++k) m.w[k] = T(0);        // lanes past n_envs: no pending packages, never finish
   T* state = reinterpret_cast<T*>(a.b.state);
   T* my_row0 = tile0 + (size_t)tid * D;
   T* my_row1 = tile1 + (size_t)tid * D;
@@ -433,50 +620,129 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
   bool any_fin = false;
   const bool latency = Mo::BULLET && c.use_latency;
   T* w = m.w;
-  // the action of step t+1 is requested while step t computes (an L2/HBM miss otherwise sits at
-  // the head of every step's dependency chain)
-  float4 a_next = make_float4(0.f, 0.f, 0.f, 0.f);
   if (state_stable) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
-  if (valid) a_next = reinterpret_cast<const float4*>(a.actions)[i];
+  // observation rows leave as one bulk copy per warp and step when the destination meets the 16-byte
+  // rules of the bulk engine for every step (else: flat coalesced copy by the warp)
+  const bool bulk = ((reinterpret_cast<uintptr_t>(a.b.obs) | (uintptr_t)((uint64_t)n * D * sizeof(T))) & 15u) == 0 &&
+                    (((uint64_t)max((int64_t)0, min((int64_t)32, n - (i - lane))) * D * sizeof(T)) & 15u) == 0;
 
   for (int t = 0; t < a.n_steps; ++t) {
     T* tn = (t & 1) ? my_row1 : my_row0;             // this step's row, previous step's row
     const T* to = (t & 1) ? my_row0 : my_row1;
     const int64_t tn_off = (int64_t)t * n;           // offset of step t in the [n_steps][n] outputs
-    bool fin = false;
+    bool fin = false, dn = false, trunc = false, state_ok = true;
     T ep_ret_out = T(0);
     int ep_len_out = 0;
     T core[C], a_new[4], actT[4];
-    int n_ep = 0;
+    const int n_ep = (int)w[L.ep_length] + 1;        // 1-based step index in the episode
+    // this step's action; the line of step t+1's action is requested now (prefetch: no register is held
+    // across the step), so that an L2/HBM miss does not sit at the head of the next step's dependency chain
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float4* ap = reinterpret_cast<const float4*>(a.actions) + tn_off + i;
+      a4 = *ap;
+      if (t + 1 < a.n_steps) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + n));
+    }
+    const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) actT[k] = (T)act[k];
+
+    // ---- this step's tile slice was last read by the warp's bulk copy of step t - n_tiles (lane 0 issues
+    // the copies of the warp, so it is the lane that can wait for them).  No block-wide barrier: warps
+    // run through their steps independently.
+    if (lane == 0) { if (NT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+    __syncwarp();
+
+    // ---- history part of the row first (it does not depend on this step's arithmetic):
+    // [o(k-H+1), a(k-H), ..., o(k-1), a(k-2)] = entries 1..H-1 of the previous row (base.py:303-319).
+    // The tile has the row-major layout of the output, so lane l's row starts at bank l*D mod 32: when D is
+    // a multiple of 16 a warp walking its rows in step hits few banks (D = 160: ONE bank).  Each lane
+    // then walks its row rotated by its lane id (bank l*(D+1) + k: conflict free).
+    // quirk (Bullet agent): after a reset the action deque holds H references to ring[-1]
+    // (agents.py:386, base.py:426-427), which the latency ring overwrites in place with the current action
+    // -> those entries read as the *current* action for as long as they stay in the deque.
+    if (valid) {
+      if constexpr (wide) {
+        for (int j = 0; j < H - 1; ++j) {
+          const bool alias = latency && (j + n_ep <= H);
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            int kk = k + lane;
+            kk = kk >= E ? kk - E : kk;
+            kk = kk >= E ? kk - E : kk;
+            T v = to[(j + 1) * E + kk];
+            if (alias && kk >= C) v = kk == C ? actT[0] : kk == C + 1 ? actT[1] : kk == C + 2 ? actT[2] : actT[3];
+            tn[j * E + kk] = v;
+          }
+        }
+      } else {
+        for (int j = 0; j < H - 1; ++j) {
+          const bool alias = latency && (j + n_ep <= H);
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            T v = to[(j + 1) * E + k];
+            if (k >= C && alias) v = actT[k >= C ? k - C : 0];
+            tn[j * E + k] = v;
+          }
+        }
+      }
+    }
 
     if (valid) {
-      const float4 a4 = a_next;
-      if (t + 1 < a.n_steps) a_next = reinterpret_cast<const float4*>(a.actions)[tn_off + n + i];
-      const float act[4] = {a4.x, a4.y, a4.z, a4.w};
       const Rng<T, RNG> rng = make_rng<T, RNG>(a, a.counter + (uint64_t)t, i,
                                                a.b.tape_step ? a.b.tape_step + (int64_t)t * c.slots_step * n : nullptr,
                                                a.dump_step ? a.dump_step + (int64_t)t * c.slots_step * n : nullptr);
-      n_ep = (int)w[L.ep_length] + 1;                // 1-based step index in the episode
       T la_prev[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { la_prev[k] = w[L.last_action + k]; actT[k] = (T)act[k]; }
+      for (int k = 0; k < 4; ++k) la_prev[k] = w[L.last_action + k];
 
       // ---- physics sub-steps; the observation call after each one is discarded by the
       // reference (base.py:464) but advances the gyro bias / low-pass state (quirk A.6-1)
       int slot = 0;
       for (int s = 0; s < c.agg; ++s) {
-        const bool full = (s % c.obs_rate) == 0;
-        m.substep(rng, act, s, slot, full);
-        slot += 4 + (NOISE ? (full ? c.slots_obs_full : c.slots_obs_gyro) : 0);
+        const bool full_obs = (s % c.obs_rate) == 0;
+        m.substep(rng, act, s, slot, full_obs);
+        slot += 4 + (NOISE ? (full_obs ? c.slots_obs_full : c.slots_obs_gyro) : 0);
       }
 
-      // ---- the observation that is returned (base.py:468 -> compute_history)
       T target[3] = {c.target[0], c.target[1], c.target[2]};
       if constexpr (TASK == PDX_TASK_CIRCLE) m.ref_point((n_ep + (int)w[L.ref_offset]) % 300, target);   // circle.py:130
       if constexpr (TASK == PDX_TASK_TAKEOFF) m.ref_point(min(n_ep * c.agg, 299), target);                // takeoff.py:108
+
+      // ---- does the episode end with this step?  Known as soon as the physics is done (compute_done,
+      // TimeLimit of __init__.py:11): a lane that will take a reset package at the end of the step asks
+      // for its cache lines NOW, a thousand instructions before it reads them.
+      {
+        T e[3], om[3];
+        m.euler(e);
+        m.body_rates(om);
+        dn = m.done(e, om, target);
+        trunc = n_ep >= c.max_episode_steps;
+        if (c.reset_on_nonfinite) {
+          // extension: a non-finite state ends the episode as a truncation that carries no reward and no cost
+          // (the collector bootstraps a truncation with V(final observation), which is sanitised below)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) state_ok = state_ok && M<T>::finite(w[L.xyz + k]);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) state_ok = state_ok && M<T>::finite(om[k]) && M<T>::finite(e[k]);
+          trunc = trunc || !state_ok;
+        }
+        fin = dn || trunc;
+        if constexpr (POOL) {
+          if (fin && c.auto_reset) {
+            const char* pk = reinterpret_cast<const char*>(
+                package_ptr<Mo>(state, n, i, H, (((int)w[L.ep_index] >> 4) + 1) & (kPackSlots - 1)));
+#pragma unroll
+            for (int b = 0; b < (int)(L.pack_quads * 4 * sizeof(T)) + 127; b += 128)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pk + b));
+          }
+        }
+      }
+
+      // ---- the observation that is returned (base.py:468 -> compute_history)
       T q_true[4] = {T(0), T(0), T(0), T(1)};
       if constexpr (!NOISE) {
         if constexpr (Mo::BULLET) { for (int k = 0; k < 4; ++k) q_true[k] = w[L.quat + k]; }
@@ -484,21 +750,48 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
       }
       m.observe(rng, SITE_FINAL_OBS, slot, target, actT, q_true, core);
 
-      // a(k-1) paired with o(k).  quirk (Bullet agent): after a reset the action deque holds H
-      // references to ring[-1] (agents.py:386, base.py:426-427), which the latency ring
-      // overwrites in place with the current action -> those entries read as the *current*
-      // action for as long as they stay in the deque.
+      // a(k-1) paired with o(k); Bullet aliasing quirk as above
       {
         const bool alias = latency && (H - 1 + n_ep <= H);
 #pragma unroll
         for (int k = 0; k < 4; ++k) a_new[k] = alias ? actT[k] : la_prev[k];
       }
+    }
 
+    // ---- newest entry of the row: [o(k), a(k-1)]
+    if constexpr (wide) {                                  // registers cannot be indexed by the rotated position:
+#pragma unroll                                             // column-major staging buffer of the warp
+      for (int k = 0; k < C; ++k) stg[k * 32 + lane] = core[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg[(C + k) * 32 + lane] = a_new[k];
+      __syncwarp();
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          int kk = k + lane;
+          kk = kk >= E ? kk - E : kk;
+          kk = kk >= E ? kk - E : kk;
+          tn[(H - 1) * E + kk] = stg[kk * 32 + lane];
+        }
+      }
+      __syncwarp();
+    } else {                                               // other strides: at most 8-way (measured faster)
+      if (valid) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
+      }
+    }
+
+    if (valid) {
       // ---- reward / cost / done
+      T target[3] = {c.target[0], c.target[1], c.target[2]};
+      if constexpr (TASK == PDX_TASK_CIRCLE) m.ref_point((n_ep + (int)w[L.ref_offset]) % 300, target);
+      if constexpr (TASK == PDX_TASK_TAKEOFF) m.ref_point(min(n_ep * c.agg, 299), target);
       T e[3], om[3];
       m.euler(e);
       m.body_rates(om);
-      const bool dn = m.done(e, om, target);
       // action penalties are float32 arithmetic in the reference (float32 action array)
       float nca2 = 0.0f;
 #pragma unroll
@@ -512,7 +805,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
         T d2 = T(0);
         if (!(latency && n_ep == 1)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { const T d = actT[k] - la_prev[k]; d2 += d * d; }
+          for (int k = 0; k < 4; ++k) { const T d = actT[k] - w[L.last_action + k]; d2 += d * d; }
         }
         par = c.arp * M<T>::sqrt(d2);
       }
@@ -525,97 +818,25 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
       const T dist = norm3(w[L.xyz] - target[0], w[L.xyz + 1] - target[1], w[L.xyz + 2] - target[2]);
       T r = -dist - penalties;
       if (TASK == PDX_TASK_TAKEOFF && w[L.xyz + 2] < T(0.08)) r -= T(1);
-      const T cst = m.cost(e, om, act);
+      T cst = m.cost(e, om, act);
 
-      // ---- episode accounting, TimeLimit (__init__.py:11)
+      // ---- episode accounting
+      if (c.reset_on_nonfinite && !state_ok) { r = T(0); cst = T(0); }
       w[L.ep_return] += r;
       w[L.ep_length] = (T)n_ep;
-      bool trunc = n_ep >= c.max_episode_steps;
-      if (c.reset_on_nonfinite) {
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) ok = ok && M<T>::finite(w[L.xyz + k]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ok = ok && M<T>::finite(om[k]) && M<T>::finite(e[k]);
-        trunc = trunc || !ok;
-      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) w[L.last_action + k] = actT[k];
       reinterpret_cast<T*>(a.b.reward)[tn_off + i] = r;
       reinterpret_cast<T*>(a.b.cost)[tn_off + i] = cst;
       a.b.terminated[tn_off + i] = dn ? 1 : 0;
       a.b.truncated[tn_off + i] = trunc ? 1 : 0;
-      fin = dn || trunc;
       ep_ret_out = w[L.ep_return];
       ep_len_out = n_ep;
       if (a.b.episode_return) reinterpret_cast<T*>(a.b.episode_return)[tn_off + i] = fin ? ep_ret_out : T(0);
       if (a.b.episode_length) a.b.episode_length[tn_off + i] = fin ? ep_len_out : 0;
     }
 
-    // ---- the tile of this step was last read by the bulk copy of step t - n_tiles: thread 0
-    // publishes the newest step whose copy has drained (it waits right after issuing each copy;
-    // with a single tile the rows are shifted in place, ascending, once the previous copy left)
-    if (t >= NT) { while (atomicAdd(s_tile_free, 0) < t - NT) {} }
-
-    // history emission: [o(k-H+1), a(k-H), ..., o(k), a(k-1)]  (base.py:303-319).
-    // The tile has the row-major layout of the output, so lane l's row starts at bank l*D mod 32:
-    // when D is a multiple of 16 a warp walking its rows in step hits few banks (D = 160: ONE
-    // bank).  Each lane then walks its row rotated by its lane id (bank l*(D+1) + k: conflict
-    // free); the new entry goes through a warp-private column-major staging buffer because
-    // registers cannot be indexed by the rotated position.
-    if ((D & 15) == 0) {                                   // >= 16-way conflicts in natural order
-      const int rot = lane;
-      if (valid) {
-        for (int j = 0; j < H - 1; ++j) {
-          const bool alias = latency && (j + n_ep <= H);
-#pragma unroll
-          for (int k = 0; k < E; ++k) {
-            int kk = k + rot;
-            kk = kk >= E ? kk - E : kk;
-            kk = kk >= E ? kk - E : kk;
-            T v = to[(j + 1) * E + kk];
-            if (alias && kk >= C) v = kk == C ? actT[0] : kk == C + 1 ? actT[1] : kk == C + 2 ? actT[2] : actT[3];
-            tn[j * E + kk] = v;
-          }
-        }
-      }
-      static_assert(E * 32 <= kResetRows * 4 * kResetChunk, "staging buffer must fit the reset table");
-      T* stg = rtab;                                       // the reset table is idle at this point
-#pragma unroll
-      for (int k = 0; k < C; ++k) stg[k * 32 + lane] = core[k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) stg[(C + k) * 32 + lane] = a_new[k];
-      __syncwarp();
-      if (valid) {
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-          int kk = k + rot;
-          kk = kk >= E ? kk - E : kk;
-          kk = kk >= E ? kk - E : kk;
-          tn[(H - 1) * E + kk] = stg[kk * 32 + lane];
-        }
-      }
-      __syncwarp();
-    } else if (valid) {                                    // other strides: at most 8-way (measured faster)
-      for (int j = 0; j < H - 1; ++j) {
-        const bool alias = latency && (j + n_ep <= H);
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-          T v = to[(j + 1) * E + k];
-          if (k >= C && alias) v = actT[k >= C ? k - C : 0];
-          tn[j * E + k] = v;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
-    }
-
-    // ---- auto-reset of finished episodes.  The reset path is as long as a step, mostly random
-    // number generation, and only a few lanes of a warp need it: the warp generates the draws of
-    // its finished environments TOGETHER (one Philox call per lane and pass, into a shared table)
-    // and only the remaining arithmetic runs divergent on the owner lanes.  No block barrier.
+    // ---- finished episodes: statistics, auto-reset
     if (fin) {
       any_fin = true;
       acc_sum[0 * B + tid] += 1.0;
@@ -628,72 +849,32 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
       acc_ext[3 * B + tid] = M<T>::fmax(acc_ext[3 * B + tid], (T)ep_len_out);
     }
     const bool do_reset = fin && c.auto_reset;
-    const unsigned ballot = __ballot_sync(0xffffffffu, do_reset);
+    const unsigned ballot = __ballot_sync(full, do_reset);
     if (ballot) {
       if (do_reset && a.b.final_obs) {                     // last observation of the episode
         T* fo = reinterpret_cast<T*>(a.b.final_obs) + (tn_off + i) * D;
-        for (int k = 0; k < D; ++k) fo[k] = tn[k];
+        if (c.reset_on_nonfinite) { for (int k = 0; k < D; ++k) fo[k] = M<T>::finite(tn[k]) ? tn[k] : T(0); }
+        else { for (int k = 0; k < D; ++k) fo[k] = tn[k]; }
       }
-      const uint64_t ctr = a.counter + (uint64_t)t;
-      T o1[C], o2[C], stale[3];
       if (do_reset) {
+        T o1[C], o2[C], stale[3];
         m.body_rates(stale);
         if (c.reset_on_nonfinite) {                        // extension: do not seed the next episode's
 #pragma unroll
           for (int k = 0; k < 3; ++k) if (!M<T>::finite(stale[k])) stale[k] = T(0);   // low pass with inf / NaN
         }
-      }
-      if constexpr (RNG == PDX_RNG_PHILOX) {
-        const int my_rank = __popc(ballot & ((1u << lane) - 1u));
-        const int total = __popc(ballot);
-        if (do_reset) s_fin_lane[my_rank] = (unsigned char)lane;
-        __syncwarp();
-        for (int chunk = 0; chunk < total; chunk += kResetChunk) {
-          const int cnt = min(kResetChunk, total - chunk);
-          // work item = (site row, finished env): consecutive lanes take consecutive envs.
-          // The rows a reset draws form four runs (task, DR, first and second observation call).
-          constexpr int n_task = TASK == PDX_TASK_TAKEOFF ? 1 : (Mo::BULLET ? 7 : 6);
-          constexpr int n_dr = Mo::BULLET ? 4 : 2, n_obs = NOISE ? 6 : 0;
-          constexpr int n_rows = n_task + n_dr + 2 * n_obs;
-          const unsigned rcp = (65536u + (unsigned)cnt - 1u) / (unsigned)cnt;
-          for (int item = lane; item < cnt * n_rows; item += 32) {
-            const int ri = (int)(((unsigned)item * rcp) >> 16), slot = item - ri * cnt;
-            const int row = ri < n_task ? ri
-                          : ri < n_task + n_dr ? (int)(SITE_DR - SITE_RESET) + ri - n_task
-                          : ri < n_task + n_dr + n_obs ? (int)(SITE_RESET_OBS1 - SITE_RESET) + ri - n_task - n_dr
-                          : (int)(SITE_RESET_OBS2 - SITE_RESET) + ri - n_task - n_dr - n_obs;
-            const uint32_t site = SITE_RESET + (uint32_t)row;
-            const int owner = (int)s_fin_lane[chunk + slot];
-            Rng<T, RNG> rr = make_rng<T, RNG>(a, ctr, block_base + (warp << 5) + owner, nullptr, nullptr);
-            const uint4 r4 = rr.raw(site);
-            T v[4];
-            if (reset_site_is_normal(site)) {
-              M<T>::box_muller(r4.x, r4.y, &v[0], &v[1]);
-              M<T>::box_muller(r4.z, r4.w, &v[2], &v[3]);
-            } else {
-              v[0] = M<T>::unit(r4.x); v[1] = M<T>::unit(r4.y); v[2] = M<T>::unit(r4.z); v[3] = M<T>::unit(r4.w);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rtab[(row * 4 + k) * kResetChunk + slot] = v[k];
-          }
-          __syncwarp();
-          if (do_reset && my_rank >= chunk && my_rank < chunk + kResetChunk) {
-            TableRng<T> tr;
-            tr.tab = rtab + (my_rank - chunk);
-            reset_env(m, tr, stale, o1, o2);
-          }
-          __syncwarp();
-        }
-      } else {
-        if (do_reset) {
-          const Rng<T, RNG> rr = make_rng<T, RNG>(a, ctr, i,
+        if constexpr (POOL) {
+          take_package(m, state, n, i, H, stale, o1, o2);
+        } else {
+          // the draws of auto-reset number e + 1 of this environment (same keys as gen_package in dump mode)
+          const int e_next = ((int)w[L.ep_index] >> 4) + 1;
+          const Rng<T, RNG> rr = make_rng<T, RNG>(a, (uint64_t)e_next, i,
                                                   a.b.tape_reset ? a.b.tape_reset + (int64_t)t * c.slots_reset * n : nullptr,
-                                                  a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr);
+                                                  a.dump_reset ? a.dump_reset + (int64_t)t * c.slots_reset * n : nullptr, true);
           reset_env(m, rr, stale, o1, o2);
+          w[L.ep_index] = (T)(16 * e_next);
         }
-      }
-      if (do_reset) {                                      // first observation of the new episode
-        for (int j = 0; j < H; ++j) {
+        for (int j = 0; j < H; ++j) {                      // first observation of the new episode
 #pragma unroll
           for (int k = 0; k < C; ++k) tn[j * E + k] = (j == H - 1) ? o2[k] : o1[k];
 #pragma unroll
@@ -701,30 +882,55 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
         }
       }
     }
-
-    // ---- observation rows of the block leave as one bulk copy (or a flat coalesced copy when
-    // the destination does not meet the 16-byte rules of the bulk engine)
-    T* gdst = reinterpret_cast<T*>(a.b.obs) + (tn_off + block_base) * D;
-    const T* tile = (t & 1) ? tile1 : tile0;
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)D * (uint32_t)sizeof(T);
-    const bool bulk = ((reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
-    if (bulk) {
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        bulk_store(gdst, tile, bytes);
-        if (NT == 2) { bulk_wait_read<1>(); atomicExch(s_tile_free, t - 1); }   // the copy issued one step ago has drained
-        else { bulk_wait_read<0>(); atomicExch(s_tile_free, t); }
+    if constexpr (POOL) {
+      // Package regeneration is decided per BLOCK, one barrier vote per step: all warps of a block run the
+      // (long) generator at the same step, and the barrier keeps them within one step of each other -- the
+      // step loop is ~30 KB of straight-line code, and warps that drift apart each stream it through the
+      // instruction caches on their own (measured: `no_instruction` became the top stall).  The vote
+      // passes when a warp has a good pass worth of packages pending (40: every lane of the pass busy), or
+      // when some environment would find its NEXT slot still pending (all kPackSlots of its packages
+      // used up since the last regeneration: a burst of very short episodes) -- so the take at the end of
+      // a step never has to wait for a package.
+      const int ew = (int)w[L.ep_index], e0 = ew >> 4, pend0 = ew & 15;
+      int total = 0;
+#pragma unroll
+      for (int sl = 0; sl < kPackSlots; ++sl) total += __popc(__ballot_sync(full, (pend0 >> sl) & 1));
+      const bool urgent = (pend0 >> ((e0 + 1) & (kPackSlots - 1))) & 1;
+      if (__syncthreads_or(urgent || total >= 40)) {
+        if (valid) m.store(state, n, i, true);             // the state is parked in its own planes around the
+        // generator: nothing is live across it (inlined on top of the live state it spilled on the hot path)
+        const int pend1 = flush_pending<T, TASK, PHYS, NOISE, RNG, PID>(a, i - lane, e0, pend0);
+        if (valid) m.load(state, n, i);
+        else {
+#pragma unroll
+          for (int k = 0; k < Mo::NW; ++k) w[k] = T(0);
+        }
+        w[L.ep_index] = (T)((ew & ~15) | pend1);
       }
-    } else {
-      __syncthreads();
-      for (int e = tid; e < rows * D; e += B) gdst[e] = tile[e];
-      __syncthreads();
-      if (tid == 0) atomicExch(s_tile_free, t);
+    }
+
+    // ---- the warp's rows of this step leave as one bulk copy (or a flat coalesced copy when the
+    // destination does not meet the 16-byte rules of the bulk engine)
+    const int64_t warp_base = i - lane;                  // first environment of this warp
+    const int rows_w = (int)max((int64_t)0, min((int64_t)32, n - warp_base));     // rows of this warp's tile slice
+    if (rows_w > 0) {
+      T* gdst = reinterpret_cast<T*>(a.b.obs) + (tn_off + warp_base) * D;
+      const T* wt = tn - lane * D;                       // this warp's slice of this step's tile
+      if (bulk) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(gdst, wt, (uint32_t)rows_w * (uint32_t)D * (uint32_t)sizeof(T));
+      } else {
+        __syncwarp();
+        for (int e = lane; e < rows_w * D; e += 32) gdst[e] = wt[e];
+        __syncwarp();
+      }
     }
   }
 
   // ---- epilogue: state and history back to HBM, statistics, drain the bulk engine
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
   if (valid) {
     m.store(state, n, i, true);
     const T* last = ((a.n_steps - 1) & 1) ? my_row1 : my_row0;
@@ -760,7 +966,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) k_rollout(const KArgs<T> a) {
       }
     }
   }
-  if (tid == 0) bulk_wait_all();
+  if (lane == 0) bulk_wait_all();
 }
 
 }  // namespace pdx

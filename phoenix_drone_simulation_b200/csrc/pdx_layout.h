@@ -11,6 +11,8 @@
 
 namespace pdx {
 
+constexpr int kPackSlots = 4;      // reset packages kept per environment (power of two: slot = package number & 3)
+
 struct Layout {
   int xyz, vel;
   int rpy, omega;          // Simple: Euler angles and body rates are the integrated state
@@ -21,6 +23,9 @@ struct Layout {
   int pid;                 // PID control modes: rate integral 3, rate last error 3, attitude integral 3,
                            // attitude last error 3 (control.py:133-134,226-227)
   int ep_return, ep_length;
+  int ep_index;            // 16 e + pend: e = number of in-kernel auto-resets this
+                           // environment has consumed (keys the reset draws), pend bit s = package slot s was
+                           // consumed and is not regenerated yet (one word: the step kernel has no register to spare)
   int ref_offset;          // circle only
   int gyro_bias, gyro_lpf; // noise only
   int n_words;             // words before the history ring
@@ -31,6 +36,9 @@ struct Layout {
                            // n_quads state quads; slot s holds entry s+1 of the last emitted
                            // observation row (= entry s of the next one), base.py:303-319
   int core_dim;            // C
+  int pack_quads;          // quads of one pre-computed reset package: the n_quads state quads of a freshly
+                           // reset environment followed by the two reset observations (2 C words).  Two
+                           // package slots per environment follow the history slots (see k_rollout)
 };
 
 constexpr int core_dim_of(int task, bool noise) {
@@ -64,6 +72,7 @@ constexpr Layout make_layout(int task, int physics, bool noise, bool pid = false
   L.pid = pid ? take(12) : -1;
   L.ep_return = take(1);
   L.ep_length = take(1);
+  L.ep_index = take(1);
   L.gyro_bias = L.gyro_lpf = -1;
   if (noise) {
     L.gyro_bias = take(3);
@@ -87,6 +96,7 @@ constexpr Layout make_layout(int task, int physics, bool noise, bool pid = false
   L.n_quads = (w + 3) / 4;
   L.core_dim = core_dim_of(task, noise);
   L.hist_quads = (L.core_dim + 4 + 3) / 4;
+  L.pack_quads = L.n_quads + (2 * L.core_dim + 3) / 4;
   return L;
 }
 

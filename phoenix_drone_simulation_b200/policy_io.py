@@ -32,9 +32,12 @@ def export_policy_json(ac, path, activation='relu'):
     return data
 
 
-def load_policy_json(path, device='cuda'):
+def load_policy_json(path, device='cuda', standardize=True, **ac_kwargs):
     """JSON file -> ActorCritic whose actor and observation scaling come from the file (the critic is
-    freshly initialised: the export does not contain it)."""
+    freshly initialised: the export does not contain it).  Any two hidden layers of up to 64 units
+    (experiments/05_impact_of_hidden_neurons trains 10 ... 64).  standardize=False drops the scaling:
+    the network then sees raw observations, which is how the file's `check_sum` known answer is defined
+    (utils/export.py:47-53: sum of net(ones)); `verify_check_sum` evaluates it."""
     with open(path) as f:
         data = json.load(f)
     layers = []
@@ -46,16 +49,44 @@ def load_policy_json(path, device='cuda'):
     if data.get('activation', 'relu') != 'relu' or len(layers) != 3:
         raise NotImplementedError('expected a relu actor with two hidden layers (ppo/defaults.py:6-19)')
     obs_dim, act_dim = layers[0][0].shape[1], layers[-1][0].shape[0]
-    ac = ActorCritic(obs_dim, act_dim=act_dim, pi_hidden=(layers[0][0].shape[0], layers[1][0].shape[0]), device=device)
+    ac = ActorCritic(obs_dim, act_dim=act_dim, pi_hidden=(layers[0][0].shape[0], layers[1][0].shape[0]), device=device,
+                     use_standardized_obs=standardize, **ac_kwargs)
     lins = [m for m in ac.pi if isinstance(m, torch.nn.Linear)]
     with torch.no_grad():
         for lin, (w, b) in zip(lins, layers):
             lin.weight.copy_(w)
             lin.bias.copy_(b)
-        sp = torch.tensor(data['scaling_parameters'], dtype=torch.float32)
-        ac.obs_oms.mean.copy_(sp[0])
-        ac.obs_oms.std.copy_(sp[1])
+        if standardize:
+            sp = torch.tensor(data['scaling_parameters'], dtype=torch.float32)
+            ac.obs_oms.mean.copy_(sp[0])
+            ac.obs_oms.std.copy_(sp[1])
+    ac.check_sum = float(data['check_sum']) if 'check_sum' in data else None
     return ac
+
+
+@torch.no_grad()
+def verify_check_sum(path, device='cuda', policy_kernel='tc', rtol=1e-5, atol=1e-5):
+    """The reference's known-answer test for an exported policy (utils/export.py:47-53 writes it,
+    utils/utils.py:324-330 is meant to check it): the sum of the network's outputs for an all-ones input
+    must equal the file's `check_sum`.  Evaluated with the fused policy kernel selected by
+    `policy_kernel` on CUDA devices (the torch modules on CPU).  Returns (got, expected)."""
+    ac = load_policy_json(path, device=device, standardize=False, policy_kernel=policy_kernel)
+    if ac.check_sum is None:
+        raise ValueError(f'{path} carries no check_sum')
+    d = ac.pi.net[0].in_features
+    ones = torch.ones((128, d), dtype=torch.float32, device=device)       # one full tensor-core tile of identical rows
+    if torch.device(device).type == 'cuda':
+        n = ones.shape[0]
+        act = torch.empty((n, 4), device=device); val = torch.empty(n, device=device)
+        logp = torch.empty(n, device=device); mu = torch.empty((n, 4), device=device)
+        ac.step_into(ones, act, val, logp, mu)
+        assert bool((mu == mu[0]).all()), 'identical rows must give identical outputs'
+        got = float(mu[0, :ac.log_std.shape[0]].double().sum())
+    else:
+        got = float(ac.pi(ones[:1]).double().sum())
+    if abs(got - ac.check_sum) > atol + rtol * abs(ac.check_sum):
+        raise AssertionError(f'check_sum mismatch: network gives {got}, file says {ac.check_sum}')
+    return got, ac.check_sum
 
 
 @torch.no_grad()

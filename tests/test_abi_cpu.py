@@ -80,9 +80,14 @@ def test_state_layout(lib):
         assert not (words & seen), name
         seen |= words
     assert len(seen) == 34                      # 28 per-step words + 6 per-episode constants
+    # bookkeeping word of the reset-package pool (4 * auto-resets consumed + pending-slot bits)
+    assert lib.pdx_state_field(C.byref(c), b'ep_index', C.byref(fw), C.byref(nw)) == 0 and nw.value == 1
+    assert fw.value not in seen
     assert lib.pdx_state_field(C.byref(c), b'hist', C.byref(fw), C.byref(nw)) == 0
     assert fw.value == 36 and nw.value == 20    # one history slot: 13 + 4 words in 5 quads
-    assert lib.pdx_state_quads(C.byref(c)) == 14
+    assert lib.pdx_state_field(C.byref(c), b'pool', C.byref(fw), C.byref(nw)) == 0
+    assert fw.value == 56 and nw.value == 4 * 16 * 4    # four reset packages: 9 state quads + 26 observation words each
+    assert lib.pdx_state_quads(C.byref(c)) == 14 + 64
     assert lib.pdx_state_field(C.byref(c), b'quat', C.byref(fw), C.byref(nw)) != 0     # Bullet only
     assert b'does not exist' in lib.pdx_last_error()
     # algorithmic bytes per env: state 34 + history 17 words read and written once

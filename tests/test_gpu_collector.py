@@ -378,3 +378,21 @@ def test_nccl_world2_running_stats_and_episode_stats():
         np.testing.assert_array_equal(async_stats, sync_stats)      # asynchronous form == synchronous form
     np.testing.assert_array_equal(res[0][1], res[1][1])
     np.testing.assert_array_equal(res[0][2], res[1][2])
+
+
+KAT_DIR = os.path.join(GOLD, 'kat_models')
+
+
+@pytest.mark.parametrize('kernel,tol', [('cuda', 1e-5), ('tc', 1e-5), ('tc_tf32', 5e-3)])
+def test_policy_kernels_reproduce_reference_check_sums(kernel, tol):
+    """Known-answer test held by the reference itself: for each exported policy, sum(net(ones)) must
+    equal the file's check_sum (utils/export.py:47-53, utils/utils.py:324-330).  All three policy kernels
+    (CUDA-core float32, tcgen05 split-TF32, tcgen05 single TF32) on six reference-exported networks
+    (D = 40, 50-50 relu).  Tolerance: float32 kernels 1e-5 abs + 1e-5 rel (the reference computed the sum
+    in float32); single TF32 5e-3 (its documented operand rounding)."""
+    from phoenix_drone_simulation_b200.policy_io import verify_check_sum
+    files = sorted(f for f in os.listdir(KAT_DIR) if f.endswith('.json'))
+    assert len(files) == 6
+    for f in files:
+        got, exp = verify_check_sum(os.path.join(KAT_DIR, f), device='cuda', policy_kernel=kernel, rtol=tol, atol=tol)
+        print(f'{f} [{kernel}]: kernel {got:.6f} vs check_sum {exp:.6f}')
