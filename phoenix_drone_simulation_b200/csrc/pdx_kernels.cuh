@@ -16,6 +16,12 @@
 #pragma once
 #include "pdx_model.cuh"
 
+#ifndef PDX_FAST2
+#define PDX_FAST2 1
+#endif
+#ifndef PDX_PREFETCH
+#define PDX_PREFETCH 1
+#endif
 #ifndef PDX_FLUSH_INLINE
 #define PDX_FLUSH_INLINE __forceinline__
 #endif
@@ -604,16 +610,22 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
+  // H = 2 with two tiles (the common case): the newest entry of a row is also the oldest entry of the NEXT
+  // row, so every entry is written twice -- into this step's tile and into the next step's -- instead of
+  // being read back and shifted (17 LDS + their latency at the head of every step)
+  const bool fast2 = PDX_FAST2 && !wide && H == 2 && NT == 2;
   if (valid) {
     m.load(state, n, i);
-    // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0)
+    // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0);
+    // fast2: straight into entry 0 of the first row
     for (int s = 0; s < H - 1; ++s) {
 #pragma unroll
       for (int qd = 0; qd < QH; ++qd) {
         T v[4];
         load_quad(state, n, i, L.n_quads + s * QH + qd, v);
 #pragma unroll
-        for (int l = 0; l < 4; ++l) if (qd * 4 + l < E) my_row1[(s + 1) * E + qd * 4 + l] = v[l];
+        for (int l = 0; l < 4; ++l)
+          if (qd * 4 + l < E) { if (fast2) my_row0[qd * 4 + l] = v[l]; else my_row1[(s + 1) * E + qd * 4 + l] = v[l]; }
       }
     }
   }
@@ -653,8 +665,10 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
     // ---- this step's tile slice was last read by the warp's bulk copy of step t - n_tiles (lane 0 issues
     // the copies of the warp, so it is the lane that can wait for them).  No block-wide barrier: warps
     // run through their steps independently.
-    if (lane == 0) { if (NT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-    __syncwarp();
+    if (!fast2) {
+      if (lane == 0) { if (NT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+      __syncwarp();
+    }
 
     // ---- history part of the row first (it does not depend on this step's arithmetic):
     // [o(k-H+1), a(k-H), ..., o(k-1), a(k-2)] = entries 1..H-1 of the previous row (base.py:303-319).
@@ -677,6 +691,11 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
             if (alias && kk >= C) v = kk == C ? actT[0] : kk == C + 1 ? actT[1] : kk == C + 2 ? actT[2] : actT[3];
             tn[j * E + kk] = v;
           }
+        }
+      } else if (fast2) {                                  // entry 0 is already there; only the aliasing quirk
+        if (latency && n_ep <= H) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tn[C + k] = actT[k];
         }
       } else {
         for (int j = 0; j < H - 1; ++j) {
@@ -736,8 +755,13 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
             const char* pk = reinterpret_cast<const char*>(
                 package_ptr<Mo>(state, n, i, H, (((int)w[L.ep_index] >> 4) + 1) & (kPackSlots - 1)));
 #pragma unroll
-            for (int b = 0; b < (int)(L.pack_quads * 4 * sizeof(T)) + 127; b += 128)
+            for (int b = 0; b < (int)(L.pack_quads * 4 * sizeof(T)) + 127; b += 128) {
+#if PDX_PREFETCH == 1
               asm volatile("prefetch.global.L1 [%0];" ::"l"(pk + b));
+#elif PDX_PREFETCH == 2
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + b));
+#endif
+            }
           }
         }
       }
@@ -776,11 +800,22 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
       }
       __syncwarp();
     } else {                                               // other strides: at most 8-way (measured faster)
+      if (fast2) {                                         // the other tile: its bulk copy (issued a step ago) must have
+        if (lane == 0) bulk_wait_read<0>();                // been read out before entry 0 of the next row goes in
+        __syncwarp();
+      }
       if (valid) {
 #pragma unroll
-      for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
+        for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
+        for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
+        if (fast2) {
+          T* nx = const_cast<T*>(to);
+#pragma unroll
+          for (int k = 0; k < C; ++k) nx[k] = core[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nx[C + k] = a_new[k];
+        }
       }
     }
 
@@ -879,6 +914,13 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
           for (int k = 0; k < C; ++k) tn[j * E + k] = (j == H - 1) ? o2[k] : o1[k];
 #pragma unroll
           for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
+        }
+        if (fast2) {
+          T* nx = const_cast<T*>(to);
+#pragma unroll
+          for (int k = 0; k < C; ++k) nx[k] = o2[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nx[C + k] = w[L.last_action + k];
         }
       }
     }

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libphoenix_b200.so')
+# PDX_LIB: another build of the same library (kernel A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get('PDX_LIB') or os.path.join(HERE, 'libphoenix_b200.so')
 ABI_VERSION = 7
 PDX_BUF_STATE_STABLE = 1          # PdxBuffers.flags
 PDX_POLICY_TC_OVERLAP = 0x100     # or-ed into pdx_policy_step_tc's precision
