@@ -231,9 +231,12 @@ typedef struct PdxMlp {
  * padded as the kernel stages them; refresh it with pdx_policy_pack after every weight update. */
 int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v);
 int pdx_policy_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, float* packed, void* stream);
+/* `env_offset`: global index of row 0 -- the action noise is keyed by the GLOBAL environment index, like the
+ * environment's own draws, so a rollout does not depend on how the environments are sharded over GPUs. */
 int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                     const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
-                    uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
+                    uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp, float* mu_out,
+                    void* stream);
 
 /* The same ActorCritic.step (algs/core.py:370-393; MLPGaussianActor core.py:227-289, MLPCritic core.py:297-310,
  * standardisation utils/online_mean_std.py:42-48) on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators
@@ -252,8 +255,50 @@ int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp
 int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision, float* packed, void* stream);
 int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                        const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, int32_t precision,
-                       uint64_t seed, uint64_t counter, float* actions, float* values, float* logp, float* mu_out,
-                       void* stream);
+                       uint64_t seed, uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp,
+                       float* mu_out, void* stream);
+
+/* ---- the fused collector step: IWPGAlgorithm.roll_out's loop (algs/iwpg/iwpg.py:350-385) in ONE launch ----
+ * For T = rollout->n_steps steps and every environment of the shard:
+ *     a, v, logp = ActorCritic.step(obs)            (algs/core.py:370-393, the networks of `policy`)
+ *     obs, r, terminated, truncated = env.step(a)   (envs/base.py:433-475, in-kernel auto-reset)
+ * followed by last_val = V(obs) (the value that bootstraps the cut at the end of the rollout, iwpg.py:376-378).
+ * The environment state stays in registers for the whole rollout and the policy networks run on the tensor
+ * cores (tcgen05, accumulators and hidden activations in tensor memory) between two env.steps of the same
+ * thread; csrc/pdx_collect.cu.  Outputs are time-major: buf->obs [T][n][obs_dim] receives the observation
+ * AFTER step t (row t + 1 of a [T+1][n][obs_dim] rollout tensor whose row 0 is rollout->obs0), buf->reward /
+ * cost / terminated / truncated [T][n], buf->final_obs (optional) [T][n][obs_dim], buf->episode_stats.
+ * Step t draws the environment noise at `counter + t` (as pdx_step_many) and the action noise at
+ * policy->counter + t with the Philox stream of pdx_policy_step_tc keyed by the GLOBAL environment index.
+ * Supported: float32, Philox, observation noise on, PWM control, the Hover and Circle ids (obs_dim <= 64 and not a
+ * multiple of 16), auto_reset; PDX_ERR_INVALID otherwise (callers then alternate pdx_policy_step_tc and pdx_step). */
+typedef struct PdxPolicy {
+  int32_t obs_dim;
+  int32_t precision;            /* 1 = operands rounded to TF32 once, 3 = split TF32 (float32-level results) */
+  const float* mean;            /* observation normaliser (utils/online_mean_std.py:42-48); std == NULL skips it */
+  const float* std;
+  float eps;
+  int32_t reserved;
+  const PdxMlp* pi;             /* Gaussian actor, two hidden layers (relu), <= 4 outputs */
+  const PdxMlp* v;              /* critic, two hidden layers (tanh), 1 output */
+  const float* log_std;         /* [n_out] */
+  const float* packed;          /* weight image of pdx_policy_tc_pack for this precision */
+  uint64_t seed, counter;       /* Philox key / position of the action noise */
+} PdxPolicy;
+typedef struct PdxRollout {
+  int32_t n_steps;              /* T */
+  int32_t reserved;
+  const float* obs0;            /* [n][obs_dim] observation the rollout starts from */
+  float* act;                   /* out [T][n][4] */
+  float* val;                   /* out [T][n]    */
+  float* logp;                  /* out [T][n]    */
+  float* last_val;              /* out [n]: V(observation after the last step) */
+  void*  scratch;               /* device scratch of at least pdx_collect_scratch_bytes(device) bytes */
+  int64_t scratch_bytes;
+} PdxRollout;
+int64_t pdx_collect_scratch_bytes(int32_t device);
+int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const PdxPolicy* policy, const PdxRollout* rollout,
+                uint64_t seed, uint64_t counter, void* stream);
 
 /* Cross-rank combination of the 8-word episode statistics (utils/mpi_tools.py:217-240 does four
  * MPI all-reduces per key): the caller all-gathers the per-rank vectors into gathered[world][8]

@@ -27,6 +27,7 @@ UNITS = {
     'pdx_abi.cu': [],
     'pdx_rollout.cu': [],
     'pdx_policy_tc.cu': [],
+    'pdx_collect.cu': ['-use_fast_math'],
 }
 
 

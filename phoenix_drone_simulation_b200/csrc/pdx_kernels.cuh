@@ -527,6 +527,43 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   }
 }
 
+// Episode statistics of a block -> the 8-word global vector: per-thread columns in shared memory
+// (n, sum ret, sum ret^2, sum len; min/max ret, min/max len), one warp-shuffle reduction and one set
+// of atomics per block and launch.  Called by ALL threads of the block (it contains a barrier).
+template <class T>
+__device__ __forceinline__ void block_reduce_episode_stats(double* gs, const double* acc_sum, const T* acc_ext, int B, bool any_fin) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (gs && __syncthreads_or(any_fin ? 1 : 0)) {
+    if (warp == 0) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (k == 4 || k == 6) ? 1e300 : (k == 5 || k == 7) ? -1e300 : 0.0;
+      for (int col = lane; col < B; col += 32) {
+        if (acc_sum[col] > 0.0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] += acc_sum[k * B + col];
+          v[4] = fmin(v[4], (double)acc_ext[0 * B + col]); v[5] = fmax(v[5], (double)acc_ext[1 * B + col]);
+          v[6] = fmin(v[6], (double)acc_ext[2 * B + col]); v[7] = fmax(v[7], (double)acc_ext[3 * B + col]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        v[4] = fmin(v[4], __shfl_xor_sync(0xffffffffu, v[4], o));
+        v[5] = fmax(v[5], __shfl_xor_sync(0xffffffffu, v[5], o));
+        v[6] = fmin(v[6], __shfl_xor_sync(0xffffffffu, v[6], o));
+        v[7] = fmax(v[7], __shfl_xor_sync(0xffffffffu, v[7], o));
+      }
+      if (lane == 0) {
+        atomicAdd(&gs[0], v[0]); atomicAdd(&gs[1], v[1]); atomicAdd(&gs[2], v[2]); atomicAdd(&gs[3], v[3]);
+        atomic_min_double(&gs[4], v[4]); atomic_max_double(&gs[5], v[5]);
+        atomic_min_double(&gs[6], v[6]); atomic_max_double(&gs[7], v[7]);
+      }
+    }
+  }
+}
+
 // ---- bulk asynchronous copy shared -> global (TMA engine), bulk-group completion ------------
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
@@ -558,109 +595,59 @@ __host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_til
   return bytes + sizeof(double) * 4 * block;
 }
 
+// per-thread context of the step loop: everything that is not the environment state itself
+template <class T>
+struct StepCtx {
+  T* state;
+  int64_t n, i;               // environments of the shard, this thread's (local) environment index
+  bool valid;                 // i < n
+  int lane, tid, B;           // lane in the warp, thread in the block, threads per block (statistics columns)
+  T* row0; T* row1;           // this thread's row in the two observation tiles (row1 == row0 with one tile)
+  T* stg;                     // column-major staging buffer of the warp (WIDE only)
+  double* acc_sum; T* acc_ext;
+  int NT;                     // observation tiles (1 or 2)
+  bool fast2, bulk, latency, any_fin;
+};
+
 // ---------------------------------------------------------------------------------------------
-//  fused multi-step env.step (+ auto-reset)
+//  ONE env.step (+ auto-reset) of every environment of the calling thread group, with the state in the
+//  registers of `m`: shared by k_rollout (open-loop action sequences) and k_collect (csrc/pdx_collect.cu:
+//  the policy step runs between two calls).  `a4`: this thread's action; outputs of step t go to row t of the
+//  time-major buffers in a.b.  `vote(pred)`: OR of `pred` over the thread group that regenerates reset
+//  packages together (a barrier: all threads of the group call it once per step).
 // ---------------------------------------------------------------------------------------------
 // WIDE: obs_dim is a multiple of 16 (rows walked in rotated order, see below) -- a template parameter
 // because as a run-time branch it made ptxas spill the 17 words of the new entry on BOTH paths.
-template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE>
-__global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE, class Vote>
+__device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, PHYS, NOISE, RNG, PID>& m, StepCtx<T>& sc,
+                                             const int t, const float4 a4, Vote vote) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
-  constexpr int C = Mo::C, E = Mo::E, QH = Mo::QH;
+  constexpr int C = Mo::C, E = Mo::E;
   constexpr bool POOL = RNG == PDX_RNG_PHILOX;       // pre-computed reset packages (see gen_package)
+  constexpr bool wide = WIDE;
   const DevCfg<T>& c = a.c;
-  const int64_t n = a.b.n_envs;
-  const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t block_base = (int64_t)blockIdx.x * B;
-  const int64_t i = block_base + tid;
-  const bool valid = i < n;
+  const int64_t n = sc.n, i = sc.i;
+  const bool valid = sc.valid, fast2 = sc.fast2, bulk = sc.bulk, latency = sc.latency;
+  const int lane = sc.lane, tid = sc.tid, B = sc.B, NT = sc.NT;
   const int D = c.obs_dim, H = c.history;
   const unsigned full = 0xffffffffu;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* tile0 = reinterpret_cast<T*>(smem_raw);
-  const int NT = a.n_tiles;
-  T* tile1 = NT == 2 ? tile0 + (size_t)B * D : tile0;
-  constexpr bool wide = WIDE;
-  T* stg = tile0 + (size_t)NT * B * D + (size_t)warp * (E * 32);          // valid only when `wide`
-  const size_t words_before_acc = (size_t)NT * B * D + (wide ? (size_t)(B >> 5) * E * 32 : 0);
-  T* acc_ext = tile0 + words_before_acc;
-  const size_t off = ((words_before_acc + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
-  double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    acc_sum[k * B + tid] = 0.0;
-    acc_ext[k * B + tid] = (k & 1) ? T(-1e30) : T(1e30);
-  }
-
-  Mo m(c);
-#pragma unroll
-  for (int k = 0; k < Mo::NW; ++k) m.w[k] = T(0);        // lanes past n_envs: no pending packages, never finish
-  T* state = reinterpret_cast<T*>(a.b.state);
-  T* my_row0 = tile0 + (size_t)tid * D;
-  T* my_row1 = tile1 + (size_t)tid * D;
-  // Programmatic dependent launch: this grid may have started while the kernel before it on the stream is
-  // still draining.  Nothing that kernel could have written is touched before griddepcontrol.wait (which
-  // returns once it has completed and its writes are visible).  With PDX_BUF_STATE_STABLE the caller
-  // guarantees that kernel does not write `state` (collector: it is the policy kernel), so the state
-  // load below runs under its tail and only the actions wait.
-  const bool state_stable = (a.b.flags & PDX_BUF_STATE_STABLE) != 0;
-  if (!state_stable) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
-  // H = 2 with two tiles (the common case): the newest entry of a row is also the oldest entry of the NEXT
-  // row, so every entry is written twice -- into this step's tile and into the next step's -- instead of
-  // being read back and shifted (17 LDS + their latency at the head of every step)
-  const bool fast2 = PDX_FAST2 && !wide && H == 2 && NT == 2;
-  if (valid) {
-    m.load(state, n, i);
-    // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0);
-    // fast2: straight into entry 0 of the first row
-    for (int s = 0; s < H - 1; ++s) {
-#pragma unroll
-      for (int qd = 0; qd < QH; ++qd) {
-        T v[4];
-        load_quad(state, n, i, L.n_quads + s * QH + qd, v);
-#pragma unroll
-        for (int l = 0; l < 4; ++l)
-          if (qd * 4 + l < E) { if (fast2) my_row0[qd * 4 + l] = v[l]; else my_row1[(s + 1) * E + qd * 4 + l] = v[l]; }
-      }
-    }
-  }
-  bool any_fin = false;
-  const bool latency = Mo::BULLET && c.use_latency;
+  T* state = sc.state;
+  T* stg = sc.stg;
+  double* acc_sum = sc.acc_sum;
+  T* acc_ext = sc.acc_ext;
   T* w = m.w;
-  if (state_stable) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
-  // observation rows leave as one bulk copy per warp and step when the destination meets the 16-byte
-  // rules of the bulk engine for every step (else: flat coalesced copy by the warp)
-  const bool bulk = ((reinterpret_cast<uintptr_t>(a.b.obs) | (uintptr_t)((uint64_t)n * D * sizeof(T))) & 15u) == 0 &&
-                    (((uint64_t)max((int64_t)0, min((int64_t)32, n - (i - lane))) * D * sizeof(T)) & 15u) == 0;
-
-  for (int t = 0; t < a.n_steps; ++t) {
-    T* tn = (t & 1) ? my_row1 : my_row0;             // this step's row, previous step's row
-    const T* to = (t & 1) ? my_row0 : my_row1;
-    const int64_t tn_off = (int64_t)t * n;           // offset of step t in the [n_steps][n] outputs
-    bool fin = false, dn = false, trunc = false, state_ok = true;
-    T ep_ret_out = T(0);
-    int ep_len_out = 0;
-    T core[C], a_new[4], actT[4];
-    const int n_ep = (int)w[L.ep_length] + 1;        // 1-based step index in the episode
-    // this step's action; the line of step t+1's action is requested now (prefetch: no register is held
-    // across the step), so that an L2/HBM miss does not sit at the head of the next step's dependency chain
-    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      const float4* ap = reinterpret_cast<const float4*>(a.actions) + tn_off + i;
-      a4 = *ap;
-      if (t + 1 < a.n_steps) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + n));
-    }
-    const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+  T* tn = (t & 1) ? sc.row1 : sc.row0;               // this step's row, previous step's row
+  const T* to = (t & 1) ? sc.row0 : sc.row1;
+  const int64_t tn_off = (int64_t)t * n;             // offset of step t in the [n_steps][n] outputs
+  bool fin = false, dn = false, trunc = false, state_ok = true;
+  T ep_ret_out = T(0);
+  int ep_len_out = 0;
+  T core[C], a_new[4], actT[4];
+  const int n_ep = (int)w[L.ep_length] + 1;          // 1-based step index in the episode
+  const float act[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) actT[k] = (T)act[k];
+  for (int k = 0; k < 4; ++k) actT[k] = (T)act[k];
 
     // ---- this step's tile slice was last read by the warp's bulk copy of step t - n_tiles (lane 0 issues
     // the copies of the warp, so it is the lane that can wait for them).  No block-wide barrier: warps
@@ -873,7 +860,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
 
     // ---- finished episodes: statistics, auto-reset
     if (fin) {
-      any_fin = true;
+      sc.any_fin = true;
       acc_sum[0 * B + tid] += 1.0;
       acc_sum[1 * B + tid] += (double)ep_ret_out;
       acc_sum[2 * B + tid] += (double)ep_ret_out * (double)ep_ret_out;
@@ -938,7 +925,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
 #pragma unroll
       for (int sl = 0; sl < kPackSlots; ++sl) total += __popc(__ballot_sync(full, (pend0 >> sl) & 1));
       const bool urgent = (pend0 >> ((e0 + 1) & (kPackSlots - 1))) & 1;
-      if (__syncthreads_or(urgent || total >= 40)) {
+      if (vote(urgent || total >= 40)) {
         if (valid) m.store(state, n, i, true);             // the state is parked in its own planes around the
         // generator: nothing is live across it (inlined on top of the live state it spilled on the hot path)
         const int pend1 = flush_pending<T, TASK, PHYS, NOISE, RNG, PID>(a, i - lane, e0, pend0);
@@ -968,6 +955,102 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
         __syncwarp();
       }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+//  fused multi-step env.step (+ auto-reset)
+// ---------------------------------------------------------------------------------------------
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE>
+__global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
+  constexpr Layout L = Mo::L;
+  constexpr int E = Mo::E, QH = Mo::QH;
+  const DevCfg<T>& c = a.c;
+  const int64_t n = a.b.n_envs;
+  const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t block_base = (int64_t)blockIdx.x * B;
+  const int64_t i = block_base + tid;
+  const bool valid = i < n;
+  const int D = c.obs_dim, H = c.history;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile0 = reinterpret_cast<T*>(smem_raw);
+  const int NT = a.n_tiles;
+  T* tile1 = NT == 2 ? tile0 + (size_t)B * D : tile0;
+  constexpr bool wide = WIDE;
+  T* stg = tile0 + (size_t)NT * B * D + (size_t)warp * (E * 32);          // valid only when `wide`
+  const size_t words_before_acc = (size_t)NT * B * D + (wide ? (size_t)(B >> 5) * E * 32 : 0);
+  T* acc_ext = tile0 + words_before_acc;
+  const size_t off = ((words_before_acc + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
+  double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc_sum[k * B + tid] = 0.0;
+    acc_ext[k * B + tid] = (k & 1) ? T(-1e30) : T(1e30);
+  }
+
+  Mo m(c);
+#pragma unroll
+  for (int k = 0; k < Mo::NW; ++k) m.w[k] = T(0);        // lanes past n_envs: no pending packages, never finish
+  T* state = reinterpret_cast<T*>(a.b.state);
+  T* my_row0 = tile0 + (size_t)tid * D;
+  T* my_row1 = tile1 + (size_t)tid * D;
+  // Programmatic dependent launch: this grid may have started while the kernel before it on the stream is
+  // still draining.  Nothing that kernel could have written is touched before griddepcontrol.wait (which
+  // returns once it has completed and its writes are visible).  With PDX_BUF_STATE_STABLE the caller
+  // guarantees that kernel does not write `state` (collector: it is the policy kernel), so the state
+  // load below runs under its tail and only the actions wait.
+  const bool state_stable = (a.b.flags & PDX_BUF_STATE_STABLE) != 0;
+  if (!state_stable) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  // H = 2 with two tiles (the common case): the newest entry of a row is also the oldest entry of the NEXT
+  // row, so every entry is written twice -- into this step's tile and into the next step's -- instead of
+  // being read back and shifted (17 LDS + their latency at the head of every step)
+  const bool fast2 = PDX_FAST2 && !wide && H == 2 && NT == 2;
+  if (valid) {
+    m.load(state, n, i);
+    // history slots -> entries 1..H-1 of the "previous row" (tile1 plays the old tile at t = 0);
+    // fast2: straight into entry 0 of the first row
+    for (int s = 0; s < H - 1; ++s) {
+#pragma unroll
+      for (int qd = 0; qd < QH; ++qd) {
+        T v[4];
+        load_quad(state, n, i, L.n_quads + s * QH + qd, v);
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (qd * 4 + l < E) { if (fast2) my_row0[qd * 4 + l] = v[l]; else my_row1[(s + 1) * E + qd * 4 + l] = v[l]; }
+      }
+    }
+  }
+  if (state_stable) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  StepCtx<T> sc;
+  sc.state = state; sc.n = n; sc.i = i; sc.valid = valid; sc.lane = lane; sc.tid = tid; sc.B = B;
+  sc.row0 = my_row0; sc.row1 = my_row1; sc.stg = stg; sc.acc_sum = acc_sum; sc.acc_ext = acc_ext; sc.NT = NT;
+  sc.fast2 = fast2; sc.latency = Mo::BULLET && c.use_latency; sc.any_fin = false;
+  // observation rows leave as one bulk copy per warp and step when the destination meets the 16-byte
+  // rules of the bulk engine for every step (else: flat coalesced copy by the warp)
+  sc.bulk = ((reinterpret_cast<uintptr_t>(a.b.obs) | (uintptr_t)((uint64_t)n * D * sizeof(T))) & 15u) == 0 &&
+            (((uint64_t)max((int64_t)0, min((int64_t)32, n - (i - lane))) * D * sizeof(T)) & 15u) == 0;
+
+  for (int t = 0; t < a.n_steps; ++t) {
+    // this step's action; the line of step t+1's action is requested now (prefetch: no register is held
+    // across the step), so that an L2/HBM miss does not sit at the head of the next step's dependency chain
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float4* ap = reinterpret_cast<const float4*>(a.actions) + (int64_t)t * n + i;
+      a4 = *ap;
+      if (t + 1 < a.n_steps) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + n));
+    }
+    // Package regeneration is voted per BLOCK: all warps of a block run the (long) generator at the same
+    // step, and the barrier keeps them within one step of each other -- the step is ~30 KB of straight-line
+    // code, and warps that drift apart each stream it through the instruction caches on their own
+    // (measured: `no_instruction` became the top stall)
+    rollout_step<T, TASK, PHYS, NOISE, RNG, PID, WIDE>(a, m, sc, t, a4, [](bool p) { return __syncthreads_or(p) != 0; });
   }
 
   // ---- epilogue: state and history back to HBM, statistics, drain the bulk engine
@@ -978,36 +1061,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
     const T* last = ((a.n_steps - 1) & 1) ? my_row1 : my_row0;
     store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) { return last[(s + 1) * E + idx]; });
   }
-  if (a.b.episode_stats && __syncthreads_or(any_fin ? 1 : 0)) {
-    if (warp == 0) {
-      double v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (k == 4 || k == 6) ? 1e300 : (k == 5 || k == 7) ? -1e300 : 0.0;
-      for (int col = lane; col < B; col += 32) {
-        if (acc_sum[col] > 0.0) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] += acc_sum[k * B + col];
-          v[4] = fmin(v[4], (double)acc_ext[0 * B + col]); v[5] = fmax(v[5], (double)acc_ext[1 * B + col]);
-          v[6] = fmin(v[6], (double)acc_ext[2 * B + col]); v[7] = fmax(v[7], (double)acc_ext[3 * B + col]);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        v[4] = fmin(v[4], __shfl_xor_sync(0xffffffffu, v[4], o));
-        v[5] = fmax(v[5], __shfl_xor_sync(0xffffffffu, v[5], o));
-        v[6] = fmin(v[6], __shfl_xor_sync(0xffffffffu, v[6], o));
-        v[7] = fmax(v[7], __shfl_xor_sync(0xffffffffu, v[7], o));
-      }
-      if (lane == 0) {
-        double* gs = a.b.episode_stats;
-        atomicAdd(&gs[0], v[0]); atomicAdd(&gs[1], v[1]); atomicAdd(&gs[2], v[2]); atomicAdd(&gs[3], v[3]);
-        atomic_min_double(&gs[4], v[4]); atomic_max_double(&gs[5], v[5]);
-        atomic_min_double(&gs[6], v[6]); atomic_max_double(&gs[7], v[7]);
-      }
-    }
-  }
+  block_reduce_episode_stats(a.b.episode_stats, acc_sum, acc_ext, B, sc.any_fin);
   if (lane == 0) bulk_wait_all();
 }
 

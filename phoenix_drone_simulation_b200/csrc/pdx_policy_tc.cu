@@ -41,16 +41,9 @@
 #include "../../include/phoenix_b200.h"
 #include "pdx_error.h"
 
-namespace {
+#include "pdx_tc.cuh"
 
-constexpr int kTile = 128;         // environments per tile = TMEM lanes = MMA M
-constexpr int kN1 = 128;           // actor 64 | critic 64
-constexpr int kB2Words = 64 * 64;
-constexpr int kBiasTileWords = 8 * (kN1 + 64 + 64);     // K = 8 bias tiles (row k = 0 carries the bias)
-constexpr int kCommonWords = 64 * 4 + 64 + 16;          // float32 layer 3: w3a[64][4], w3c[64], b3[16]
-constexpr uint32_t kLboA = 2048 + 16;   // bytes between K chunks of the X tile (+16: bank spread for the 128-bit stores)
-constexpr uint32_t kSbo = 128;          // bytes between 8-row groups: core matrices are packed
-constexpr uint32_t kOnesBytes = 2 * 2048;
+namespace {
 
 struct TcArgs {
   int64_t n;
@@ -62,144 +55,10 @@ struct TcArgs {
   const float* log_std;
   const float* packed;
   uint64_t seed, counter;
+  int64_t env_offset;
   float* act; float* val; float* logp; float* mu;
   int64_t n_tiles;
 };
-
-// ---------------------------------------------------------------------------------------------
-//  PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint
-// expires) instead of returning at once -- a bare try_wait loop spins, and the spinning warps take issue
-// slots and shared-memory pipe bandwidth from the warps that work (37 % of all instructions, measured)
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)
-      : "memory");
-  return ok != 0;
-}
-// bounded: a tensor-core operation that never completes (a malformed descriptor) must not hang the GPU
-__device__ __forceinline__ void mbar_wait_thread(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0; !mbar_try(bar, parity); ++it)
-    if (it > (1u << 20)) __trap();
-}
-// warp-level wait: ONE lane polls (32 lanes hitting the same mbarrier word serialise), the warp
-// re-converges on __syncwarp, which also orders the other lanes' later reads after the acquire
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait_thread(bar, parity);
-  __syncwarp();
-}
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_free(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {            // warp-uniform call, elected lane commits
-  asm volatile(
-      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
-      : "memory");
-}
-
-// shared-memory matrix descriptor, no swizzle, K-major canonical layout:
-//   element (row, k) of a 4-byte type lives at  (k / 4) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 4) * 4
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-// instruction descriptor, kind::tf32: D = f32, A = B = tf32, both K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
-}
-
-// Called by ALL lanes of the issuing warp with warp-uniform operands (they then live in uniform registers);
-// elect.sync picks one lane and only the tcgen05 instruction itself is predicated on it.
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-// 32 lanes x 32 bit x 16 columns: thread l of the warp gets columns [c, c+16) of lane (base lane + l)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// round to nearest (ties away) onto the 10 explicit mantissa bits of tf32: two integer operations
-// (cvt.rna.tf32.f32 expands to an eight-instruction sequence with special-value handling)
-__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ float tanh_mufu(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Box-Muller on two 32-bit words with single MUFU operations (lg2, sqrt, sin, cos), the construction the
-// float32 step kernel uses (pdx_math.cuh); k_policy (pdx_rollout.cu) uses the same, so both policy kernels
-// draw identical actions for the same (seed, counter, env).
-__device__ __forceinline__ void pdx_policy_box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
-  const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));     // (0,1]
-  const float u2 = __uint_as_float(0x3f800000u | (b >> 9)) - 1.0f;     // [0,1)
-  float l2, r, s, c;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // -2 ln u1
-  const float ang = 6.283185307179586f * u2;
-  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
-  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
-  *z0 = r * c;
-  *z1 = r * s;
-}
-
-__device__ __forceinline__ uint4 tc_philox(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
-}
 
 // ---------------------------------------------------------------------------------------------
 //  Packed weight image (global == shared layout), floats:
@@ -210,7 +69,6 @@ __device__ __forceinline__ uint4 tc_philox(uint4 ctr, uint2 key) {
 //  B?[kc][n][j] = W[n][4 kc + j]  (torch nn.Linear weight is [out][in]): exactly the no-swizzle K-major
 //  core-matrix layout with SBO = 128 B and LBO = 16 N bytes.  Bb?[0][n][0] = bias[n], rest zero.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kBiasTileWords; }
 
 struct PackArgs {
   int32_t obs_dim, k1, x3;
@@ -291,15 +149,6 @@ struct TcCfg {
   // TMEM column regions: R0 = D1 -> a2 (hi), R1 = D2 (first K half), R2 = a2 lo, R3 = D2 (second K half)
   static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256, kR3 = 384;     // kR3 only with kSplit = 2
 };
-
-// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA; saturates correctly
-// (ex2 -> inf gives rcp -> 0) so no clamp is needed; ~1e-6 absolute error
-__device__ __forceinline__ float tanh_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(2.885390081777927f * x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-  return fmaf(-2.0f, r, 1.0f);
-}
 
 // a2 = act(D1) for this thread's 2 x CW columns, written back in place as layer 2's A operand (hi) and,
 // for X3, the lo halves into region R2.
@@ -633,8 +482,8 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
       // same (seed, counter, env).
       float eps[4] = {0.f, 0.f, 0.f, 0.f}, lp = 0.0f;
       if (cg == 0) {
-        const int64_t i = env0 + row;
-        const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+        const uint64_t i = (uint64_t)(a.env_offset + env0 + row);
+        const uint4 rr = tc_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)(i >> 32), 0x504F4Cu),
                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
         pdx_policy_box_muller(rr.x, rr.y, &eps[0], &eps[1]);
         pdx_policy_box_muller(rr.z, rr.w, &eps[2], &eps[3]);
@@ -756,8 +605,8 @@ extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMl
 
 extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                                   const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, int32_t precision,
-                                  uint64_t seed, uint64_t counter, float* actions, float* values, float* logp, float* mu_out,
-                                  void* stream) {
+                                  uint64_t seed, uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp,
+                                  float* mu_out, void* stream) {
   const int32_t overlap = (precision & PDX_POLICY_TC_OVERLAP) ? 1 : 0;
   precision &= ~PDX_POLICY_TC_OVERLAP;
   if (n <= 0 || !obs || !log_std || !packed || !actions || !values || !logp || !tc_shapes_ok(obs_dim, pi, v, precision))
@@ -769,7 +618,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   a.n = n; a.obs_dim = obs_dim; a.k1 = (obs_dim + 7) & ~7; a.act_dim = pi->n_out;
   a.flags = overlap;
   a.obs = obs; a.mean = mean; a.std = std; a.eps = eps; a.log_std = log_std; a.packed = packed;
-  a.seed = seed; a.counter = counter; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
+  a.seed = seed; a.counter = counter; a.env_offset = env_offset; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
   a.n_tiles = (n + kTile - 1) / kTile;
   const size_t smem = tc_smem_bytes(a.k1, obs_dim, x3);
   int dev = 0;

@@ -217,6 +217,7 @@ struct PolArgs {
   const float* log_std;
   const float* packed;      // [pi_words + v_words] packed weights (k_pack_policy)
   uint64_t seed, counter;
+  int64_t env_offset;       // global index of row 0: the action noise does not depend on the sharding
   float* act; float* val; float* logp; float* mu;
 };
 
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(kPolBlock) k_policy(const PolArgs a) {
   run_net<HP>(pi_net, row, nmean, ninv, D, a.pi_h1, a.pi_h2, false, hid, tid, mu);
   run_net<HV>(v_net, row, nmean, ninv, D, a.v_h1, a.v_h2, true, hid, tid, vv);
   // ---- sample: a = mu + std * eps, log p = sum(-eps^2/2 - log_std - log(2 pi)/2)
-  const uint4 r = pol_philox(make_uint4((uint32_t)i, (uint32_t)a.counter, (uint32_t)((uint64_t)i >> 32), 0x504F4Cu),
+  const uint64_t ig = (uint64_t)(a.env_offset + i);
+  const uint4 r = pol_philox(make_uint4((uint32_t)ig, (uint32_t)a.counter, (uint32_t)(ig >> 32), 0x504F4Cu),
                              make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
   // Box-Muller with single MUFU operations (lg2, sqrt, sin, cos) -- the construction of the float32 step
   // kernel (pdx_math.cuh) and of k_policy_tc, so both policy kernels draw identical actions
@@ -357,7 +359,7 @@ int launch_policy(const PolArgs& a, cudaStream_t st) {
 
 static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                            const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
-                           uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream);
+                           uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp, float* mu_out, void* stream);
 
 extern "C" int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v) {
   if (obs_dim <= 0 || !pi || !v) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_pack_words: bad argument");
@@ -367,19 +369,19 @@ extern "C" int64_t pdx_policy_pack_words(int32_t obs_dim, const PdxMlp* pi, cons
 
 extern "C" int pdx_policy_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, float* packed, void* stream) {
   if (!packed) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_pack: null buffer");
-  return policy_dispatch(0, obs_dim, packed, nullptr, nullptr, 0.f, pi, v, packed, packed, 0, 0, packed, packed, packed, nullptr, stream);
+  return policy_dispatch(0, obs_dim, packed, nullptr, nullptr, 0.f, pi, v, packed, packed, 0, 0, 0, packed, packed, packed, nullptr, stream);
 }
 
 extern "C" int pdx_policy_step(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                                const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
-                               uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
+                               uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp, float* mu_out, void* stream) {
   if (n <= 0) return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: n must be positive");
-  return policy_dispatch(n, obs_dim, obs, mean, std, eps, pi, v, log_std, packed, seed, counter, actions, values, logp, mu_out, stream);
+  return policy_dispatch(n, obs_dim, obs, mean, std, eps, pi, v, log_std, packed, seed, counter, env_offset, actions, values, logp, mu_out, stream);
 }
 
 static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const float* mean, const float* std, float eps,
                            const PdxMlp* pi, const PdxMlp* v, const float* log_std, const float* packed, uint64_t seed,
-                           uint64_t counter, float* actions, float* values, float* logp, float* mu_out, void* stream) {
+                           uint64_t counter, int64_t env_offset, float* actions, float* values, float* logp, float* mu_out, void* stream) {
   if (n < 0 || obs_dim <= 0 || !obs || !pi || !v || !log_std || !packed || !actions || !values || !logp)
     return pdx::set_error(PDX_ERR_INVALID, "pdx_policy_step: null buffer or bad size");
   if (pi->hidden[0] < 1 || pi->hidden[0] > kHidMax || pi->hidden[1] < 1 || pi->hidden[1] > kHidMax || pi->n_out < 1 || pi->n_out > 4)
@@ -393,7 +395,7 @@ static int policy_dispatch(int64_t n, int32_t obs_dim, const float* obs, const f
   a.pi_h1 = pi->hidden[0]; a.pi_h2 = pi->hidden[1]; a.v_h1 = v->hidden[0]; a.v_h2 = v->hidden[1];
   a.obs = obs; a.mean = mean; a.std = std; a.eps = eps;
   for (int k = 0; k < 3; ++k) { a.pi_w[k] = pi->weight[k]; a.pi_b[k] = pi->bias[k]; a.v_w[k] = v->weight[k]; a.v_b[k] = v->bias[k]; }
-  a.log_std = log_std; a.packed = packed; a.seed = seed; a.counter = counter;
+  a.log_std = log_std; a.packed = packed; a.seed = seed; a.counter = counter; a.env_offset = env_offset;
   a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;
   const bool pi_small = a.pi_h1 <= 52 && a.pi_h2 <= 52;
   return pi_small ? launch_policy<52, 64>(a, (cudaStream_t)stream) : launch_policy<64, 64>(a, (cudaStream_t)stream);

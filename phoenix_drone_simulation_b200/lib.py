@@ -70,6 +70,18 @@ class PdxMlp(C.Structure):
                 ('weight', C.c_void_p * 3), ('bias', C.c_void_p * 3)]
 
 
+class PdxPolicy(C.Structure):
+    _fields_ = [('obs_dim', C.c_int32), ('precision', C.c_int32), ('mean', C.c_void_p), ('std', C.c_void_p),
+                ('eps', C.c_float), ('reserved', C.c_int32), ('pi', C.POINTER(PdxMlp)), ('v', C.POINTER(PdxMlp)),
+                ('log_std', C.c_void_p), ('packed', C.c_void_p), ('seed', C.c_uint64), ('counter', C.c_uint64)]
+
+
+class PdxRollout(C.Structure):
+    _fields_ = [('n_steps', C.c_int32), ('reserved', C.c_int32), ('obs0', C.c_void_p), ('act', C.c_void_p),
+                ('val', C.c_void_p), ('logp', C.c_void_p), ('last_val', C.c_void_p), ('scratch', C.c_void_p),
+                ('scratch_bytes', C.c_int64)]
+
+
 _lib = None
 
 
@@ -108,15 +120,18 @@ def load():
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_moments.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_policy_step.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, P(PdxMlp), P(PdxMlp),
-                                    C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
     lib.pdx_policy_pack_words.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp)]
     lib.pdx_policy_pack_words.restype = C.c_int64
     lib.pdx_policy_pack.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp), C.c_void_p, C.c_void_p]
     lib.pdx_stats_combine.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_policy_step_tc.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, P(PdxMlp), P(PdxMlp),
-                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pdx_collect_scratch_bytes.argtypes = [C.c_int32]
+    lib.pdx_collect_scratch_bytes.restype = C.c_int64
+    lib.pdx_collect.argtypes = [P(PdxConfig), P(PdxBuffers), P(PdxPolicy), P(PdxRollout), C.c_uint64, C.c_uint64, C.c_void_p]
     lib.pdx_policy_tc_pack_words.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp), C.c_int32]
     lib.pdx_policy_tc_pack_words.restype = C.c_int64
     lib.pdx_policy_tc_pack.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp), C.c_int32, C.c_void_p, C.c_void_p]
@@ -139,5 +154,5 @@ EXPORTED_SYMBOLS = [
     'pdx_step_bytes', 'pdx_rollout_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step',
     'pdx_step_many', 'pdx_dump_draws',
     'pdx_gae', 'pdx_moments', 'pdx_stats_combine', 'pdx_policy_step', 'pdx_policy_pack', 'pdx_policy_pack_words',
-    'pdx_policy_step_tc', 'pdx_policy_tc_pack', 'pdx_policy_tc_pack_words',
+    'pdx_policy_step_tc', 'pdx_policy_tc_pack', 'pdx_policy_tc_pack_words', 'pdx_collect', 'pdx_collect_scratch_bytes',
 ]

@@ -242,6 +242,9 @@ class ActorCritic(torch.nn.Module):
         self.fused = (fused and len(pi_hidden) == 2 and len(v_hidden) == 2 and max(*pi_hidden, *v_hidden) <= 64
                       and act_dim <= 4)
         self.seed, self._counter = int(seed), 0
+        # global index of row 0 of the observation batches (the collector sets it from its VecEnv): the action
+        # noise is keyed by the GLOBAL environment index, so a rollout does not depend on the sharding
+        self.env_offset = 0
         self.pi = _Actor([obs_dim, *pi_hidden, act_dim], torch.nn.ReLU)
         self.v = _Net([obs_dim, *v_hidden, 1], torch.nn.Tanh)
         self.to(device)
@@ -316,8 +319,8 @@ class ActorCritic(torch.nn.Module):
         L = _lib.load()
         if self.tc_precision:
             prec = self.tc_precision | (_lib.PDX_POLICY_TC_OVERLAP if overlap else 0)
-            return L.pdx_policy_step_tc(*head[:10], prec, head[10], counter, *tail, stream)
-        return L.pdx_policy_step(*head, counter, *tail, stream)
+            return L.pdx_policy_step_tc(*head[:10], prec, head[10], counter, self.env_offset, *tail, stream)
+        return L.pdx_policy_step(*head, counter, self.env_offset, *tail, stream)
 
     @torch.no_grad()
     def step_into(self, obs, act, val, logp, mu=None):
@@ -423,6 +426,11 @@ class RolloutCollector:
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs = None
         self._prepared = None
+        self.ac.env_offset = env.env_offset
+        self.last_val = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.use_fused_kernel = True           # pdx_collect: policy + env.step of the whole rollout in ONE launch
+        self.fused_used = False                # did the last collect() run through pdx_collect?
+        self._final_obs_T = None               # [T, N, D], only when truncations can occur inside a rollout
 
     def _fused(self, generator=None):
         return (self.ac.fused and generator is None and self.env.dtype == torch.float32
@@ -453,6 +461,61 @@ class RolloutCollector:
             pool = pool or g.pool()
             self._graphs.append(g)
 
+    def _may_truncate(self):
+        """Can an episode hit the time limit (or the non-finite guard) inside a rollout?"""
+        return (not self.reset_each_rollout) or self.T >= self.env.max_episode_steps or bool(self.env.cfg.reset_on_nonfinite)
+
+    def _collect_fused(self):
+        """The whole rollout in ONE launch (pdx_collect): returns False when the configuration is outside the
+        fused kernel's plan (the caller then alternates the policy and env.step kernels)."""
+        env, ac, T = self.env, self.ac, self.T
+        if not (self.use_fused_kernel and ac.tc_precision in (1, 3) and env.rng == 'philox' and env.pdx.observation_noise
+                and env.pdx.control_mode == 0 and env.pdx.task != _lib.PDX_TASK['takeoff'] and env.obs_dim % 16 != 0
+                and env.obs_dim <= 64 and env.pdx.auto_reset):
+            return False
+        L = _lib.load()
+        p = lambda t: t.data_ptr() if t is not None else None
+        stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        pi, v = ac._mlp_struct(ac.pi, ac.log_std.shape[0]), ac._mlp_struct(ac.v, 1)
+        pack = ac._packed_weights(env.obs_dim, pi, v, stream)
+        if ac.tc_precision not in (1, 3):          # the shapes fell outside the tensor-core plan while packing
+            return False
+        may_trunc = self._may_truncate()
+        if may_trunc and self._final_obs_T is None:
+            self._final_obs_T = torch.zeros((T, env.num_envs, env.obs_dim), dtype=env.dtype, device=env.device)
+        buf = _lib.PdxBuffers.from_buffer_copy(env._buf)
+        buf.obs, buf.reward, buf.cost = p(self.obs[1:]), p(self.rew), p(self.cost)
+        buf.terminated, buf.truncated = p(self.term), p(self.trunc)
+        buf.final_obs = p(self._final_obs_T) if may_trunc else None
+        buf.episode_return = buf.episode_length = None
+        oms = ac.obs_oms
+        pol = _lib.PdxPolicy()
+        pol.obs_dim, pol.precision = env.obs_dim, ac.tc_precision
+        pol.mean, pol.std, pol.eps = (p(oms.mean), p(oms.std), oms.eps) if oms is not None else (None, None, 0.0)
+        pol.pi, pol.v = C.pointer(pi), C.pointer(v)
+        pol.log_std, pol.packed = p(ac.log_std.data), p(pack)
+        pol.seed, pol.counter = ac.seed, ac._counter + 1
+        out = _lib.PdxRollout()
+        out.n_steps, out.obs0 = T, p(self.obs[0])
+        out.act, out.val, out.logp, out.last_val = p(self.act), p(self.val), p(self.logp), p(self.last_val)
+        if getattr(self, '_scratch', None) is None:
+            self._scratch = torch.empty(int(L.pdx_collect_scratch_bytes(env.device.index)), dtype=torch.uint8, device=env.device)
+        out.scratch, out.scratch_bytes = p(self._scratch), self._scratch.numel()
+        rc = L.pdx_collect(C.byref(env.pdx), C.byref(buf), C.byref(pol), C.byref(out), env.seed, env._counter + 1, stream)
+        if rc == -1:                               # PDX_ERR_INVALID: outside the fused plan
+            return False
+        _lib.check(rc)
+        env._counter += T
+        ac._counter += T
+        if may_trunc:
+            # time-limit truncations bootstrap with V(last observation of the episode), iwpg.py:371-380: rare
+            # (once per max_episode_steps and environment), so they are gathered after the launch
+            idx = self.trunc.view(-1).nonzero().squeeze(-1)
+            if idx.numel():
+                rows = self._final_obs_T.view(T * env.num_envs, -1)[idx].float().contiguous()
+                self.boot.view(-1)[idx] = ac.value(rows)
+        return True
+
     def collect(self, generator=None):
         env, ac, T = self.env, self.ac, self.T
         torch.cuda.nvtx.range_push('pdx_collect')
@@ -465,6 +528,9 @@ class RolloutCollector:
         self.boot.zero_()
         limit = env.max_episode_steps
         fused = self._fused(generator)
+        self.fused_used = fused and self._collect_fused()
+        if self.fused_used:
+            return self._finish(self.last_val)
         graphs = self.use_cuda_graphs and generator is None and not fused
         if graphs and self._graphs is None:
             self._capture()
@@ -496,7 +562,10 @@ class RolloutCollector:
             # truncates when an episode reaches max_episode_steps, i.e. not before step `limit`
             if (not self.reset_each_rollout) or t + 1 >= limit or env.cfg.reset_on_nonfinite:
                 self.boot[t] = ac.value(env.final_obs) * self.trunc[t].float()
-        last_val = ac.value(self.obs[T])
+        return self._finish(ac.value(self.obs[T]))
+
+    def _finish(self, last_val):
+        env, ac, T = self.env, self.ac, self.T
         # iwpg.py:371-380: a time-limit hit bootstraps even if the env also terminated
         done = torch.where(self.trunc > 0, torch.full_like(self.term, 2), self.term)
         ret_std = ac.ret_oms.std if ac.ret_oms is not None else None

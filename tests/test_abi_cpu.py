@@ -175,8 +175,15 @@ def test_tensor_core_policy_shape_checks_need_no_device(lib):
     assert lib.pdx_policy_tc_pack_words(160, C.byref(pi), C.byref(v), 3) == -1         # too wide
     assert lib.pdx_policy_tc_pack_words(34, C.byref(mlp(65, 50, 4)), C.byref(v), 3) == -1
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(mlp(64, 64, 2)), 3) == -1
-    assert lib.pdx_policy_step_tc(0, 34, None, None, None, 0.0, C.byref(pi), C.byref(v), None, None, 3, 0, 0,
+    assert lib.pdx_policy_step_tc(0, 34, None, None, None, 0.0, C.byref(pi), C.byref(v), None, None, 3, 0, 0, 0,
                                   None, None, None, None, None) == -1
+    # the fused collector validates its arguments before it touches the device
+    c = pds.EnvConfig('DroneTakeOffSimpleEnv-v0').to_pdx()
+    pol, out, b = L.PdxPolicy(), L.PdxRollout(), L.PdxBuffers()
+    assert lib.pdx_collect(C.byref(c), C.byref(b), C.byref(pol), C.byref(out), 0, 0, None) == -1      # take-off rows are 48 wide
+    assert b'pdx_collect' in lib.pdx_last_error()
+    lib.pdx_collect_scratch_bytes.restype = C.c_int64
+    assert lib.pdx_collect_scratch_bytes(0) >= 148 * 512 * 48
 
 
 def test_flag_constants_match_the_header():

@@ -396,3 +396,65 @@ def test_policy_kernels_reproduce_reference_check_sums(kernel, tol):
     for f in files:
         got, exp = verify_check_sum(os.path.join(KAT_DIR, f), device='cuda', policy_kernel=kernel, rtol=tol, atol=tol)
         print(f'{f} [{kernel}]: kernel {got:.6f} vs check_sum {exp:.6f}')
+
+
+@pytest.mark.parametrize('env_id,kernel', [('DroneHoverBulletEnv-v0', 'tc'), ('DroneHoverBulletEnv-v0', 'tc_tf32'),
+                                            ('DroneCircleSimpleEnv-v0', 'tc'), ('DroneHoverSimpleEnv-v0', 'tc_tf32')])
+def test_fused_collector_kernel_is_policy_kernel_plus_env_kernel(env_id, kernel):
+    """pdx_collect (policy networks on the tensor cores + env.step, whole rollout in one launch, state in
+    registers) against its two halves run separately:
+      * every stored (value, action, log-prob) equals what the stand-alone policy kernel gives on the stored
+        observation with the same Philox counter (float32-level kernels 2e-5; single TF32: 1e-2);
+      * replaying the stored actions through the single-step env kernel from the same initial state gives the
+        stored observations / rewards / flags (same step body, other instantiation: 4e-6 x (1 + |value|), flags
+        equal), i.e. IWPGAlgorithm.roll_out's loop (iwpg.py:350-385) was executed in order;
+      * last_val = V(obs[T]), episode statistics equal those of the replay.
+    5,000 environments: several passes' worth of tiles incl. a ragged one; T = 24."""
+    from phoenix_drone_simulation_b200 import VecEnv
+    from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
+    N, T = 5000, 24
+    tol = 2e-5 if kernel == 'tc' else 1e-2
+    torch.manual_seed(4)
+    env = VecEnv(env_id, N, seed=21, keep_final_obs=True, env_offset=640)
+    twin = VecEnv(env_id, N, seed=21, keep_final_obs=True, env_offset=640)
+    ac = ActorCritic(env.obs_dim, policy_kernel=kernel, seed=5)
+    with torch.no_grad():
+        ac.obs_oms.mean.copy_(torch.randn(env.obs_dim, device='cuda') * 0.1)
+        ac.obs_oms.std.copy_(torch.rand(env.obs_dim, device='cuda') * 0.5 + 0.75)
+        for net in (ac.pi, ac.v):
+            for m in net:
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.3, 0.3)
+    ac.set_log_std(0.4)
+    col = RolloutCollector(env, ac, T)
+    c0 = ac._counter
+    data = col.collect()
+    assert col.fused_used, 'pdx_collect was not used'
+    assert torch.isfinite(col.obs).all() and torch.isfinite(col.val).all() and torch.isfinite(col.logp).all()
+    # ---- policy half
+    act2 = torch.empty((N, 4), device='cuda'); val2 = torch.empty(N, device='cuda'); lp2 = torch.empty(N, device='cuda')
+    worst_p = 0.0
+    for t in range(T):
+        ac._launch_into(col.obs[t].contiguous(), act2, val2, lp2, None, counter=c0 + 1 + t)
+        worst_p = max(worst_p, float((act2 - col.act[t]).abs().max()), float((val2 - col.val[t]).abs().max()))
+        torch.testing.assert_close(lp2, col.logp[t], rtol=1e-5, atol=1e-5)
+    assert worst_p <= tol, worst_p
+    torch.testing.assert_close(ac.value(col.obs[T].contiguous()), col.last_val, rtol=tol, atol=tol)
+    # ---- env half
+    assert torch.equal(twin.reset(), col.obs[0])
+    worst_e, n_fin = 0.0, 0
+    rel = lambda x, y: float(((x - y).abs() / (1.0 + y.abs())).max())
+    for t in range(T):
+        o, r, te, tr, info = twin.step(col.act[t].contiguous())
+        assert torch.equal(te, col.term[t].bool()) and torch.equal(tr, col.trunc[t].bool()), t
+        worst_e = max(worst_e, rel(col.obs[t + 1], o), rel(col.rew[t], r))
+        assert torch.equal(info['cost'], col.cost[t])
+        n_fin += int((te | tr).sum())
+    assert worst_e <= 4e-6, worst_e
+    assert n_fin > 0 and data['episode_stats'].n == n_fin == int(twin.episode_stats()[0])
+    # the state written back at the end of the pass (the reset-package pool may differ: the fused kernel
+    # regenerates packages per 128-environment tile, the step kernel per block)
+    for name in ('xyz', 'vel', 'ou', 'last_action', 'ep_length', 'gyro_bias', 'gyro_lpf', 'dt', 'mass'):
+        torch.testing.assert_close(env.get_state(name), twin.get_state(name), rtol=1e-5, atol=1e-5)
+    assert torch.equal(env.get_state('ep_index') // 16, twin.get_state('ep_index') // 16)       # auto-resets consumed
+    print(f'{env_id} [{kernel}]: fused vs policy kernel {worst_p:.2e}, fused vs env kernel {worst_e:.2e}, {n_fin} episodes')
