@@ -214,6 +214,15 @@ int pdx_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint
 int pdx_moments(int64_t rows, int32_t dim, const float* x, const double* shift,
                 double* out, void* stream);
 
+/* OnlineMeanStd.update (utils/online_mean_std.py:70-95) from the column sums of pdx_moments / pdx_collect, in place on
+ * the device: s1[dim] = sum (x - shift), s2[dim] = sum (x - shift)^2 over `rows` local rows (shift NULL = 0); `world`
+ * ranks with equal batch sizes.  Single rank: phase 3.  Several ranks (the reference averages the batch mean and the
+ * batch second moment over the ranks, mpi_tools.py:199-214): phase 0 writes batch_mean[dim] -> caller all-reduces it
+ * to the rank average -> phase 1 writes batch_var[dim] -> caller averages it -> phase 2 updates mean / std / count. */
+int pdx_oms_update(int32_t dim, const double* s1, const double* s2, double rows, int32_t world, const float* shift,
+                   float* batch_mean, float* batch_var, float* mean, float* std, float* count, int32_t phase,
+                   void* stream);
+
 /* ActorCritic.step (algs/core.py:370-393) fused into one launch: standardise the observation
  * ((o - mean) / (std + eps), utils/online_mean_std.py:42-48; std == NULL skips it), Gaussian actor
  * MLP (two hidden layers, relu), critic MLP (two hidden layers, tanh), a = mu + exp(log_std) * N(0,1)
@@ -295,6 +304,9 @@ typedef struct PdxRollout {
   float* last_val;              /* out [n]: V(observation after the last step) */
   void*  scratch;               /* device scratch of at least pdx_collect_scratch_bytes(device) bytes */
   int64_t scratch_bytes;
+  double* obs_moments;          /* in/out, optional [2][obs_dim]: += sum (o - mean), += sum (o - mean)^2 over the T x n  */
+                                /* observations the policy saw (mean = policy->mean, 0 without normaliser): what         */
+                                /* OnlineMeanStd.update needs (utils/online_mean_std.py:70-84), without a pass over obs  */
 } PdxRollout;
 int64_t pdx_collect_scratch_bytes(int32_t device);
 int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const PdxPolicy* policy, const PdxRollout* rollout,

@@ -48,6 +48,7 @@ struct CollectArgs {
   float* act; float* val; float* logp;       // [T][n][4], [T][n], [T][n]
   float* last_val;                           // [n]
   unsigned char* scratch;                    // per-thread episode-statistics columns of every CTA (global memory)
+  double* obs_moments;                       // optional [2][D]: sum (o - mean), sum (o - mean)^2 over the T x n policy inputs
 };
 
 template <bool X3>
@@ -62,7 +63,7 @@ __host__ __device__ inline int64_t collect_w_words(int k1) { return (int64_t)k1 
 
 // shared-memory plan (bytes), in this order
 struct ColSmem {
-  size_t ctrl, norm, bias, common, weights, x, tiles, total;
+  size_t ctrl, norm, bias, common, weights, x, tiles, moments, total;
 };
 template <bool X3>
 __host__ __device__ inline ColSmem collect_smem(int k1, int D, int warps) {
@@ -77,7 +78,8 @@ __host__ __device__ inline ColSmem collect_smem(int k1, int D, int warps) {
   s.x = (s.x + 127) & ~(size_t)127;
   s.tiles = s.x + (size_t)ColCfg<X3>::kSlots * ColCfg<X3>::kImages * (k1 / 4) * kLboA;
   s.tiles = (s.tiles + 15) & ~(size_t)15;
-  s.total = s.tiles + (size_t)warps * 32 * D * 4;
+  s.moments = (s.tiles + (size_t)warps * 32 * D * 4 + 15) & ~(size_t)15;
+  s.total = s.moments + (size_t)warps * 2 * 64 * 8;     // per warp: 64 column sums and 64 sums of squares (doubles)
   return s;
 }
 // Episode statistics accumulate in per-thread columns (n, sum ret, sum ret^2, sum len as doubles; four extrema
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   float* bw = reinterpret_cast<float*>(smem + sp.weights);         // B1, B2a, B2c (hi) [, the same (lo)]
   unsigned char* xbuf = smem + sp.x;
   T* tile0 = reinterpret_cast<T*>(smem + sp.tiles);
+  double* mom = reinterpret_cast<double*>(smem + sp.moments) + (size_t)warp * 128;   // this warp's [2][64] column moments
   double* acc_sum = reinterpret_cast<double*>(p.scratch + (size_t)blockIdx.x * collect_scratch_per_cta(B));
   T* acc_ext = reinterpret_cast<T*>(acc_sum + 4 * B);
   const uint32_t bar_w = smem_u32(mbar);
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
 
   // ---- one-time setup
   if (warp == 0) tmem_alloc<512>(smem_u32(tmem_holder));
-  if (tid == 32) {
+  if (tid == 0) {                                            // (a CTA may be a single warp)
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2 * Cfg::kSlots; ++s) mbar_init(bar_w + 8 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -174,6 +177,8 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
     acc_sum[k * B + tid] = 0.0;
     acc_ext[k * B + tid] = (k & 1) ? T(-1e30) : T(1e30);
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mom[lane + 32 * k] = 0.0;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -393,6 +398,25 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         p.val[o] = v;
         p.logp[o] = lp;
       }
+      // ---- running-statistics sums of the policy inputs (OnlineMeanStd.update,
+      // utils/online_mean_std.py:70-84, is fed with the T x n observations the policy saw): each lane sums its
+      // columns over the warp's 32 rows -- float32 over the 32 rows, float64 from there on; shifted by the
+      // normaliser's mean so that the sum of squares does not cancel
+      if (p.obs_moments) {                                      // (the slot is free again: off the tiles' critical path)
+        const int rows_w = (int)max((int64_t)0, min((int64_t)32, n - (i - lane)));
+        const T* wrow = my_row - lane * D;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = lane + 32 * h;
+          if (col < D) {
+            const float cshift = norm[col].x;
+            float s1 = 0.0f, s2 = 0.0f;
+            for (int r = 0; r < rows_w; ++r) { const float d = wrow[r * D + col] - cshift; s1 += d; s2 = fmaf(d, d, s2); }
+            mom[col] += (double)s1;
+            mom[64 + col] += (double)s2;
+          }
+        }
+      }
       // =========================== env.step of this thread's environment ===========================
       rollout_step<T, TASK, PHYS, true, PDX_RNG_PHILOX, false, false>(
           a, m, sc, t, make_float4(av[0], av[1], av[2], av[3]), [&](bool pred) { return tile_vote(bar_id, tile_threads, pred); });
@@ -405,6 +429,15 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   }
   // any episode finished in any pass of this CTA?  acc_sum[0..B) > 0 tells
   block_reduce_episode_stats(a.b.episode_stats, acc_sum, acc_ext, B, acc_sum[tid] > 0.0);
+  if (p.obs_moments) {                                          // (the reduction above contains a block barrier)
+    const double* all = reinterpret_cast<const double*>(smem + sp.moments);
+    for (int k = tid; k < 2 * D; k += B) {
+      const int col = k % D, which = k / D;
+      double v = 0.0;
+      for (int wv = 0; wv < (B >> 5); ++wv) v += all[(size_t)wv * 128 + 64 * which + col];
+      atomicAdd(&p.obs_moments[k], v);
+    }
+  }
   if (lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
@@ -486,6 +519,7 @@ extern "C" int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const Pd
   p.pol_seed = pol->seed; p.pol_counter = pol->counter;
   p.act = out->act; p.val = out->val; p.logp = out->logp; p.last_val = out->last_val;
   p.scratch = reinterpret_cast<unsigned char*>(out->scratch);
+  p.obs_moments = out->obs_moments;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, buf->device);
   const bool x3 = pol->precision == 3, bullet = c.physics == PDX_PHYSICS_BULLET, circle = c.task == PDX_TASK_CIRCLE;

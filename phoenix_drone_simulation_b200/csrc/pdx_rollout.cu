@@ -84,6 +84,37 @@ __global__ void k_stats_combine(int world, const double* __restrict__ gathered, 
   out[k] = v;
 }
 
+// OnlineMeanStd.update (utils/online_mean_std.py:70-95) from column sums, one thread per column.  The reference's
+// algebra, including its rank averages: phase 0 writes the local batch mean (float32), phase 1 -- after the caller
+// averaged it over the ranks -- the local batch second moment about the NEW mean, phase 2 -- after the second
+// average -- updates mean / std / count in place; phase 3 = all three at once for a single rank.
+__global__ void k_oms_update(int dim, const double* __restrict__ s1, const double* __restrict__ s2, double rows, double world,
+                             const float* __restrict__ shift, float* __restrict__ bmean, float* __restrict__ bvar,
+                             float* __restrict__ mean, float* __restrict__ std, float* __restrict__ count, int phase) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase == 4) {                 // the count is shared by all columns: bumped by a launch of its own, after the update
+    if (d == 0) count[0] = count[0] + (float)(rows * world);
+    return;
+  }
+  if (d < dim) {
+    const double c = shift ? (double)shift[d] : 0.0;
+    const double S1 = s1[d] + rows * c, S2 = s2[d] + 2.0 * c * s1[d] + rows * c * c;      // sums of x, x^2
+    const float n_A = count[0], n_B = (float)(rows * world), n_AB = n_A + n_B;
+    if (phase == 0 || phase == 3) bmean[d] = (float)(S1 / rows);
+    if (phase == 0) return;
+    const float delta = bmean[d] - mean[d];
+    const float mean_new = mean[d] + delta * n_B / n_AB;
+    if (phase == 1 || phase == 3) {
+      const double mm = (double)mean_new;
+      bvar[d] = (float)fmax((S2 - 2.0 * mm * S1 + rows * mm * mm) / rows, 0.0);
+    }
+    if (phase == 1) return;
+    const float M2 = n_A * std[d] * std[d] + n_B * bvar[d] + delta * delta * (n_A * n_B / n_AB);
+    mean[d] = mean_new;
+    std[d] = sqrtf(M2 / n_AB);
+  }
+}
+
 // The library carries its own static CUDA runtime: select the device the data lives on.
 int select_device_of(const void* ptr, int* dev_out = nullptr) {
   int ndev = 0;
@@ -141,6 +172,20 @@ extern "C" int pdx_moments(int64_t rows, int32_t dim, const float* x, const doub
   const size_t smem = 2ull * bx * by * sizeof(double);
   k_moments<<<grid, block, smem, (cudaStream_t)stream>>>(rows, dim, x, shift, out);
   return launch_status("pdx_moments");
+}
+
+extern "C" int pdx_oms_update(int32_t dim, const double* s1, const double* s2, double rows, int32_t world, const float* shift,
+                              float* batch_mean, float* batch_var, float* mean, float* std, float* count, int32_t phase,
+                              void* stream) {
+  if (dim <= 0 || !s1 || !s2 || rows <= 0 || world < 1 || !batch_mean || !batch_var || !mean || !std || !count || phase < 0 || phase > 3)
+    return pdx::set_error(PDX_ERR_INVALID, "pdx_oms_update: bad argument");
+  const int rc = select_device_of(mean);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((dim + 127) / 128);
+  k_oms_update<<<grid, 128, 0, (cudaStream_t)stream>>>(dim, s1, s2, rows, (double)world, shift, batch_mean, batch_var, mean, std, count, phase);
+  if (phase >= 2)
+    k_oms_update<<<1, 32, 0, (cudaStream_t)stream>>>(dim, s1, s2, rows, (double)world, shift, batch_mean, batch_var, mean, std, count, 4);
+  return launch_status("pdx_oms_update");
 }
 
 extern "C" int pdx_stats_combine(int32_t world, const double* gathered, double* out, void* stream) {

@@ -79,7 +79,7 @@ class PdxPolicy(C.Structure):
 class PdxRollout(C.Structure):
     _fields_ = [('n_steps', C.c_int32), ('reserved', C.c_int32), ('obs0', C.c_void_p), ('act', C.c_void_p),
                 ('val', C.c_void_p), ('logp', C.c_void_p), ('last_val', C.c_void_p), ('scratch', C.c_void_p),
-                ('scratch_bytes', C.c_int64)]
+                ('scratch_bytes', C.c_int64), ('obs_moments', C.c_void_p)]
 
 
 _lib = None
@@ -125,6 +125,8 @@ def load():
     lib.pdx_policy_pack_words.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp)]
     lib.pdx_policy_pack_words.restype = C.c_int64
     lib.pdx_policy_pack.argtypes = [C.c_int32, P(PdxMlp), P(PdxMlp), C.c_void_p, C.c_void_p]
+    lib.pdx_oms_update.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.pdx_stats_combine.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pdx_policy_step_tc.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, P(PdxMlp), P(PdxMlp),
                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
@@ -154,5 +156,5 @@ EXPORTED_SYMBOLS = [
     'pdx_step_bytes', 'pdx_rollout_bytes', 'pdx_device_count', 'pdx_init', 'pdx_reset', 'pdx_step',
     'pdx_step_many', 'pdx_dump_draws',
     'pdx_gae', 'pdx_moments', 'pdx_stats_combine', 'pdx_policy_step', 'pdx_policy_pack', 'pdx_policy_pack_words',
-    'pdx_policy_step_tc', 'pdx_policy_tc_pack', 'pdx_policy_tc_pack_words', 'pdx_collect', 'pdx_collect_scratch_bytes',
+    'pdx_policy_step_tc', 'pdx_policy_tc_pack', 'pdx_policy_tc_pack_words', 'pdx_collect', 'pdx_collect_scratch_bytes', 'pdx_oms_update',
 ]

@@ -80,7 +80,19 @@ class EpisodeStats:
     """mean / std / min / max of EpRet and mean of EpLen like EpochLogger.get_stats."""
 
     def __init__(self, stats):
-        s = [float(v) for v in stats.detach().cpu().tolist()]
+        self._stats = stats                       # device tensor: read back (one sync) when a value is first asked for
+
+    def __getattr__(self, name):
+        if name.startswith('_'):
+            raise AttributeError(name)
+        self._materialise()
+        try:
+            return self.__dict__[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def _materialise(self):
+        s = [float(v) for v in self._stats.detach().cpu().tolist()]
         self.n = int(s[0])
         if self.n:
             self.ret_mean = s[1] / s[0]
@@ -147,20 +159,49 @@ class OnlineMeanStd(torch.nn.Module):
     @torch.no_grad()
     def update(self, x):
         x = x.reshape(-1, self.mean.shape[0])
-        rows = x.shape[0]
-        n_B = float(rows * _world(self.dist))
-        n_A = self.count.clone()
-        n_AB = self.count + n_B
         # ONE pass over the batch: sum x and sum x^2 in float64; the second moment about the new mean
         # follows as sum x^2 - 2 m sum x + rows m^2 (same value as the reference's second pass)
         s1, s2 = self._moments(x, None)
+        self.update_from_sums(s1, s2, x.shape[0])
+
+    @torch.no_grad()
+    def update_from_sums(self, s1, s2, rows, shift=None):
+        """The same update from column sums computed elsewhere (the fused collector kernel accumulates them while
+        it rolls out): s1 = sum (x - shift), s2 = sum (x - shift)^2 over `rows` rows, float64.  On CUDA tensors
+        the algebra runs in one small kernel (pdx_oms_update) per phase -- one launch for a single rank, three
+        with the two rank averages of the reference in between -- instead of ~25 element-wise torch launches."""
+        P = _world(self.dist)
+        if s1.is_cuda:
+            dim = self.mean.shape[0]
+            if getattr(self, '_bm', None) is None:
+                self._bm = torch.empty(dim, dtype=torch.float32, device=self.mean.device)
+                self._bv = torch.empty(dim, dtype=torch.float32, device=self.mean.device)
+            p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+            s1, s2 = s1.contiguous(), s2.contiguous()
+            sh = shift.float().contiguous() if shift is not None else None
+            st = C.c_void_p(torch.cuda.current_stream(s1.device).cuda_stream)
+            call = lambda phase: _lib.check(_lib.load().pdx_oms_update(
+                dim, p(s1), p(s2), float(rows), P, p(sh), p(self._bm), p(self._bv), p(self.mean.data), p(self.std.data),
+                p(self.count.data), phase, st))
+            if P == 1:
+                call(3)
+            else:
+                call(0); self._avg(self._bm); call(1); self._avg(self._bv); call(2)
+            return
+        if shift is not None:
+            c = shift.double()
+            s2 = s2 + 2.0 * c * s1 + rows * c * c
+            s1 = s1 + rows * c
+        n_B = float(rows * P)
+        n_A = self.count.clone()
+        n_AB = self.count + n_B
         batch_mean = self._avg((s1 / rows).float())
         delta = batch_mean - self.mean
         mean_new = self.mean + delta * n_B / n_AB
         m = mean_new.double()
         batch_var = self._avg(((s2 - 2.0 * m * s1 + rows * m * m) / rows).clamp_min(0.0).float())
         M2 = n_A * self.std ** 2 + n_B * batch_var + delta ** 2 * (n_A * n_B / n_AB)
-        # in place: CUDA graphs of the policy forward hold these tensors
+        # in place: prepared launches of the policy kernels hold these tensors
         self.mean.copy_(mean_new)
         self.count.copy_(n_AB)
         self.std.copy_(torch.sqrt(M2 / n_AB))
@@ -431,6 +472,7 @@ class RolloutCollector:
         self.use_fused_kernel = True           # pdx_collect: policy + env.step of the whole rollout in ONE launch
         self.fused_used = False                # did the last collect() run through pdx_collect?
         self._final_obs_T = None               # [T, N, D], only when truncations can occur inside a rollout
+        self._obs_moments = None
 
     def _fused(self, generator=None):
         return (self.ac.fused and generator is None and self.env.dtype == torch.float32
@@ -501,6 +543,10 @@ class RolloutCollector:
         if getattr(self, '_scratch', None) is None:
             self._scratch = torch.empty(int(L.pdx_collect_scratch_bytes(env.device.index)), dtype=torch.uint8, device=env.device)
         out.scratch, out.scratch_bytes = p(self._scratch), self._scratch.numel()
+        self._obs_moments = None
+        if oms is not None:                        # the running-statistics sums of the rollout, accumulated in-kernel
+            self._obs_moments = (torch.zeros(2 * env.obs_dim, dtype=torch.float64, device=env.device), oms.mean.clone())
+            out.obs_moments = p(self._obs_moments[0])
         rc = L.pdx_collect(C.byref(env.pdx), C.byref(buf), C.byref(pol), C.byref(out), env.seed, env._counter + 1, stream)
         if rc == -1:                               # PDX_ERR_INVALID: outside the fused plan
             return False
@@ -575,11 +621,17 @@ class RolloutCollector:
         torch.cuda.nvtx.range_pop()
         return {'obs': self.obs[:T], 'act': self.act, 'adv': adv, 'target_v': target_v, 'log_p': self.logp,
                 'discounted_ret': disc_ret, 'rew': self.rew, 'val': self.val, 'done': done,
-                'episode_stats': EpisodeStats(stats)}
+                'episode_stats': EpisodeStats(stats),
+                'obs_moments': self._obs_moments if self.fused_used else None}
 
     def update_running_statistics(self, data):
         """iwpg.py:387-396: after the update phase, on the raw observations / discounted returns."""
         if self.ac.obs_oms is not None:
-            self.ac.obs_oms.update(data['obs'])
+            mom = data.get('obs_moments')
+            if mom is not None:                    # sums accumulated by pdx_collect: no pass over the observations
+                d = self.env.obs_dim
+                self.ac.obs_oms.update_from_sums(mom[0][:d], mom[0][d:], self.T * self.env.num_envs, shift=mom[1])
+            else:
+                self.ac.obs_oms.update(data['obs'])
         if self.ac.ret_oms is not None:
             self.ac.ret_oms.update(data['discounted_ret'].reshape(-1, 1))
