@@ -400,20 +400,22 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
       }
       // ---- running-statistics sums of the policy inputs (OnlineMeanStd.update,
       // utils/online_mean_std.py:70-84, is fed with the T x n observations the policy saw): each lane sums its
-      // columns over the warp's 32 rows -- float32 over the 32 rows, float64 from there on; shifted by the
-      // normaliser's mean so that the sum of squares does not cancel
+      // columns over the warp's 32 rows; the sums are kept about the normaliser's mean
       if (p.obs_moments) {                                      // (the slot is free again: off the tiles' critical path)
         const int rows_w = (int)max((int64_t)0, min((int64_t)32, n - (i - lane)));
         const T* wrow = my_row - lane * D;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = lane + 32 * h;
-          if (col < D) {
-            const float cshift = norm[col].x;
+          if (col < D && rows_w > 0) {
+            // float32 sums about the warp's own first row (tiny differences for a nearly constant column: no
+            // cancellation), moved to the common shift in float64
+            const float cw = wrow[col];
             float s1 = 0.0f, s2 = 0.0f;
-            for (int r = 0; r < rows_w; ++r) { const float d = wrow[r * D + col] - cshift; s1 += d; s2 = fmaf(d, d, s2); }
-            mom[col] += (double)s1;
-            mom[64 + col] += (double)s2;
+            for (int r = 1; r < rows_w; ++r) { const float d = wrow[r * D + col] - cw; s1 += d; s2 = fmaf(d, d, s2); }
+            const double dc = (double)cw - (double)norm[col].x, nr = (double)rows_w;
+            mom[col] += (double)s1 + nr * dc;
+            mom[64 + col] += (double)s2 + 2.0 * dc * (double)s1 + nr * dc * dc;
           }
         }
       }
