@@ -313,34 +313,47 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
-def ppo_rollout_leg(dev, n=131072, T=64, rollouts=3):
-    """BASELINE.json configs[4] next to the headline: DroneHoverBulletEnv-v0 driving a PPO rollout on this
-    GPU -- tcgen05 tensor-core policy step, fused env.step kernel, GAE and running statistics, all on
-    device (bench_configs.py measures the same per policy kernel and under torchrun)."""
+def ppo_rollout_leg(dev, n=131072, T=64, rollouts=4):
+    """BASELINE.json configs[4] next to the headline: DroneHoverBulletEnv-v0 driving a PPO rollout on this GPU:
+    IWPGAlgorithm.roll_out's loop in ONE persistent kernel per rollout (pdx_collect: policy networks on the
+    tcgen05 tensor cores between two env.steps of a thread, environment state in registers), then GAE and the
+    running statistics, all on device.  Reported per operand precision of the policy networks and, for
+    comparison, for the two-kernel path (policy kernel and env.step kernel alternating);
+    bench_configs.py measures the same under torchrun."""
     import torch
     from phoenix_drone_simulation_b200 import VecEnv
     from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
-    torch.manual_seed(0)
-    env = VecEnv('DroneHoverBulletEnv-v0', n, device=dev, seed=2, keep_final_obs=True)
-    ac = ActorCritic(env.obs_dim, device=dev)
-    col = RolloutCollector(env, ac, T)
-    for _ in range(3):                  # the first programmatic-dependent launches of a process carry a one-time cost
-        col.update_running_statistics(col.collect())
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(rollouts):
-        data = col.collect()
-        col.update_running_statistics(data)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    return {'workload': f'DroneHoverBulletEnv-v0, {n} envs x {T} steps per rollout, reference PPO networks (pi 50-50 relu, '
-                        'v 64-64 tanh): policy step + env.step + GAE + running statistics (BASELINE.json configs[4])',
-            'value': rollouts * T * n / (ms * 1e-3), 'unit': UNIT, 'ms_per_rollout': ms / rollouts,
-            'policy_kernel': {3: 'k_policy_tc (tcgen05, split TF32)', 1: 'k_policy_tc (tcgen05, single TF32)',
-                              0: 'k_policy (CUDA cores)'}[ac.tc_precision],
-            'gpu_launches_per_rollout': 2 * T + 3}
+
+    def run(kernel, fused):
+        torch.manual_seed(0)
+        env = VecEnv('DroneHoverBulletEnv-v0', n, device=dev, seed=2, keep_final_obs=True)
+        ac = ActorCritic(env.obs_dim, device=dev, policy_kernel=kernel)
+        col = RolloutCollector(env, ac, T)
+        col.use_fused_kernel = fused
+        for _ in range(3):              # the first programmatic-dependent launches of a process carry a one-time cost
+            col.update_running_statistics(col.collect())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rollouts):
+            data = col.collect()
+            col.update_running_statistics(data)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        assert col.fused_used == fused
+        return {'value': rollouts * T * n / (ms * 1e-3), 'unit': UNIT, 'ms_per_rollout': ms / rollouts,
+                'gpu_launches_per_rollout': (1 if fused else 2 * T) + 8}
+
+    out = {'workload': f'DroneHoverBulletEnv-v0, {n} envs x {T} steps per rollout, reference PPO networks (pi 50-50 relu, '
+                       'v 64-64 tanh): policy step + env.step + GAE + running statistics (BASELINE.json configs[4])'}
+    names = {'tc': 'split TF32 (float32-level results)', 'tc_tf32': 'single TF32 (1e-3 relative on mu / v)'}
+    for kernel in ('tc', 'tc_tf32'):
+        out[f'pdx_collect, {names[kernel]}'] = run(kernel, True)
+    out[f'k_policy_tc + k_rollout alternating, {names["tc_tf32"]}'] = run('tc_tf32', False)
+    best = max((v for v in out.values() if isinstance(v, dict)), key=lambda r: r['value'])
+    out['value'], out['unit'] = best['value'], UNIT
+    return out
 
 
 class DistCtx:
@@ -359,7 +372,19 @@ class DistCtx:
             # carries ONE JSON line, so NCCL's log goes to stderr unless the caller chose a file.
             if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
                 os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
-            dist.init_process_group('nccl', device_id=self.device)
+            # NCCL prints its version banner with printf on fd 1 whatever NCCL_DEBUG_FILE says: fd 1 points at
+            # stderr while the communicator comes up (init + first collective), then stdout is restored
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group('nccl', device_id=self.device)
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
             self.dist = dist
         else:
             self.dist = None

@@ -76,7 +76,7 @@ def _dist():
     return dist, dist.get_rank(), dist.get_world_size()
 
 
-def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
+def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc', fused=True):
     """BASELINE configs[4]: n environments PER GPU; under torchrun every rank owns its shard (env_offset) and
     the running statistics / episode statistics are combined over NCCL inside the timed region; the
     time is the max over ranks."""
@@ -86,6 +86,7 @@ def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
     env = VecEnv('DroneHoverBulletEnv-v0', n, device=dev, seed=2, keep_final_obs=True, env_offset=rank * n)
     ac = ActorCritic(env.obs_dim, device=env.device, policy_kernel=policy_kernel, dist=dist, seed=10000 * rank)
     col = RolloutCollector(env, ac, T, dist=dist)
+    col.use_fused_kernel = fused
     for _ in range(warmup):
         data = col.collect()
         col.update_running_statistics(data)
@@ -112,8 +113,10 @@ def ppo_rollout(n, T, rollouts, warmup, policy_kernel='tc'):
     kern = {'tc': 'tcgen05 tensor-core kernel, split-TF32 (float32-level)', 'tc_tf32': 'tcgen05 tensor-core kernel, single TF32',
             'cuda': 'CUDA-core float32 kernel'}[policy_kernel]
     return {'env_id': 'DroneHoverBulletEnv-v0', 'envs': n, 'n_gpus': world, 'rollout_steps': T, 'policy_kernel': policy_kernel,
-            'what': f'PPO rollout: fused policy step ({kern}), fused env.step kernel writing into [T,N,.] buffers, '
-                    'GAE kernel, running-stat moments',
+            'fused_collector_kernel': bool(col.fused_used),
+            'what': (f'PPO rollout: pdx_collect, one persistent kernel per rollout (policy networks: {kern}; env.step with the state in '
+                     'registers), GAE kernel, running statistics' if col.fused_used else
+                     f'PPO rollout: policy step ({kern}) and env.step kernel alternating, GAE kernel, running-stat moments'),
             'env_steps_per_s': rollouts * T * n / (ms * 1e-3), 'ms_per_rollout': ms / rollouts, 'wall_s': wall,
             'episodes_in_last_rollout': es.n, 'ep_ret_mean': es.ret_mean, 'ep_len_mean': es.len_mean}
 
