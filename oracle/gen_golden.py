@@ -109,8 +109,14 @@ def run_reference(env_id, kwargs, actions_kind, T, seed, record=True, max_episod
     ctx = rec if record else _Null()
     with ctx:
         init_tape = rec.new_phase()
-        env = gym.make(env_id, **kwargs)
+        # `use_ground_effect` is not a constructor argument of the reference: its physics classes carry the flag
+        # (physics.py:18,24) but nothing ever sets it.  The golden switches it on by hand so that the reference's own
+        # calculate_ground_effect (physics.py:27-58) and its use in step_forward (physics.py:117-120) are recorded.
+        ref_kwargs = {k: v for k, v in kwargs.items() if k != 'use_ground_effect'}
+        env = gym.make(env_id, **ref_kwargs)
         u = env.unwrapped
+        if kwargs.get('use_ground_effect'):
+            u.physics.use_ground_effect = True
         actions = make_actions(actions_kind, T, u.drone.HOVER_ACTION, seed + 1)
         reset_tapes, step_tapes = [], []
         obs, rew, term, cost, state = [], [], [], [], []
@@ -198,6 +204,11 @@ CASES = [
     ('hover_bullet_h3', 'DroneHoverBulletEnv-v0', dict(observation_history_size=3), 'mixed', 150, 43),
     ('circle_bullet_default', 'DroneCircleBulletEnv-v0', {}, 'mixed', 300, 51),
     ('takeoff_bullet_default', 'DroneTakeOffBulletEnv-v0', {}, 'takeoff', 300, 61),
+    # --- ground effect (physics.py:27-58,117-120; the flag is forced on, see run_reference): take-off starts on the
+    # ground where the effect is largest; the hover case flies at 1 m where it is ~1e-4 of the thrust ---
+    ('takeoff_bullet_groundeffect', 'DroneTakeOffBulletEnv-v0', dict(use_ground_effect=True), 'takeoff', 300, 62),
+    ('takeoff_bullet_groundeffect_det', 'DroneTakeOffBulletEnv-v0', dict(DET, use_ground_effect=True), 'takeoff', 300, 63),
+    ('hover_bullet_groundeffect', 'DroneHoverBulletEnv-v0', dict(use_ground_effect=True), 'mixed', 150, 64),
     # --- PID control modes (experiments/07 uses agg 4 / 8 with the Bullet ids) ---
     ('hover_simple_attrate', 'DroneHoverSimpleEnv-v0', dict(control_mode='AttitudeRate'), 'pid', 300, 71),
     ('hover_simple_attitude_det', 'DroneHoverSimpleEnv-v0', dict(DET, control_mode='Attitude'), 'pid', 300, 72),
@@ -212,7 +223,10 @@ def main():
     check_recorder()
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]                      # optional: names of the cases to (re)generate
     for name, env_id, kwargs, kind, T, seed in CASES:
+        if only and name not in only:
+            continue
         g = run_reference(env_id, kwargs, kind, T, seed)
         np.savez_compressed(os.path.join(out_dir, name + '.npz'), **g)
         print(f'{name:34s} T={T} resets={len(g["reset_after"])} obs_dim={g["obs"].shape[1]} '

@@ -284,6 +284,7 @@ class OracleEnv:
         z0 = 0.0125 if self.task == 'takeoff' else 1.0
         self.init_xyz = np.array([0, 0, z0], dtype=np.float32)       # float32! hover.py:44
         self.init_quat = quat_from_euler_unnormalised(np.zeros(3))
+        self.init_xyz_dot, self.init_rpy_dot = np.zeros(3), np.zeros(3)      # base.py:117-118
 
         # --- persistent state ---
         self.xyz = np.array([0., 0., 1.])
@@ -577,8 +578,8 @@ class OracleEnv:
     def _task_reset(self):
         s = self.src
         pos = self.init_xyz.copy()                   # float32 array (A.6-6)
-        vel = np.zeros(3)
-        omega_s = np.zeros(3)
+        vel = np.array(self.init_xyz_dot, dtype=np.float64)          # hover.py:196-197 (zeros unless a caller set
+        omega_s = np.array(self.init_rpy_dot, dtype=np.float64)      # them: simopt/pybullet.py:147-154)
         quat = self.init_quat.copy()
         if self.task == 'takeoff':                   # takeoff.py:179-212
             if self.reset_dist:

@@ -59,7 +59,8 @@ def rot_from_quat(q):
 class TrajectoryObjective:
     """observations [M, T, 12] = (xyz, xyz_dot, rpy, body rates) logs, actions [M, T, 4] in [-1, 1],
     pre_inputs [M, P, 4]; `evaluate(candidates [K, 2] = (thrust-to-weight, motor time constant))`
-    returns the K objective values of simopt/pybullet.py:72-128."""
+    returns the K objective values of simopt/pybullet.py:72-128; `evaluate(..., per_trajectory=True)` the
+    [K, M] losses of evaluate_once (pybullet.py:130-183) themselves."""
 
     def __init__(self, observations, actions, pre_inputs, env_id='DroneHoverBulletEnv-v0', device='cuda',
                  dtype=torch.float64, gamma=0.95, seed=0, **env_kwargs):
@@ -79,7 +80,7 @@ class TrajectoryObjective:
         return self._env
 
     @torch.no_grad()
-    def evaluate(self, candidates):
+    def evaluate(self, candidates, per_trajectory=False):
         cand = torch.as_tensor(candidates, dtype=torch.float64, device=self.device).reshape(-1, 2)
         K, M, T = cand.shape[0], self.M, self.T
         env = self._make(K * M)
@@ -92,13 +93,16 @@ class TrajectoryObjective:
         env.set_state('motor_k', (0.028 * 9.81 * t2w / 4).repeat_interleave(M)[:, None].expand(-1, 4))
         for j in range(self.pre.shape[1]):
             env.step(rep(self.pre[:, j]).contiguous())
-        # 2) logged initial state: pose, velocities (body rates -> world frame), cleared latency ring
+        # 2) logged initial state: pose, velocities, cleared latency ring.  quirk kept (verified against the reference,
+        # tests/golden_collector/simopt_hover.npz): evaluate_once stores R w_logged as init_rpy_dot
+        # (pybullet.py:153-154) and task_specific_reset hands R^T init_rpy_dot to Bullet as the WORLD rate
+        # (hover.py:242) -- the logged body rates end up as the world angular velocity, unrotated
         x0 = rep(self.obs[:, 0])
         q = quat_from_euler(x0[:, 6:9])
         env.set_state('xyz', x0[:, 0:3])
         env.set_state('vel', x0[:, 3:6])
         env.set_state('quat', q)
-        env.set_state('omega_world', torch.einsum('nij,nj->ni', rot_from_quat(q), x0[:, 9:12]))
+        env.set_state('omega_world', x0[:, 9:12])
         for name, width in (('ring', 8), ('ring_idx', 1), ('last_action', 4), ('ep_length', 1), ('ep_return', 1)):
             env.set_state(name, torch.zeros((K * M, width), dtype=torch.float64, device=self.device))
         # 3) replay the logged actions in one fused launch
@@ -119,4 +123,5 @@ class TrajectoryObjective:
         L = err.abs().sum(-1) + err.norm(dim=-1)
         w = self.gamma ** torch.arange(T - 1, dtype=torch.float64, device=self.device)
         per_traj = (L * w[:, None]).mean(0)                                                # np.mean(errs)
-        return per_traj.reshape(K, M).mean(1)
+        per_traj = per_traj.reshape(K, M)
+        return per_traj if per_trajectory else per_traj.mean(1)

@@ -472,3 +472,76 @@ def test_fused_collector_kernel_is_policy_kernel_plus_env_kernel(env_id, kernel,
     torch.testing.assert_close(ac.obs_oms.mean, ref.obs_oms.mean, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(ac.obs_oms.std, ref.obs_oms.std, rtol=1e-5, atol=1e-6)
     print(f'{env_id} [{kernel}]: fused vs policy kernel {worst_p:.2e}, fused vs env kernel {worst_e:.2e}, {n_fin} episodes')
+
+
+def test_simopt_objective_matches_reference_losses():
+    """TrajectoryObjective (K candidates x M mini-trajectories in one reset, five single-step launches and ONE fused
+    launch) against the losses the UNMODIFIED reference's evaluate_once gave for every (candidate, mini-trajectory)
+    pair (simopt/pybullet.py:130-225; tests/golden_collector/simopt_hover.npz).  float64 engine: 1e-9."""
+    from phoenix_drone_simulation_b200.simopt import TrajectoryObjective
+    g = _load('simopt_hover')
+    obj = TrajectoryObjective(g['observations'], g['actions'], g['pre_inputs'], motor_thrust_noise=0.0)
+    L = obj.evaluate(g['candidates'][:, :2], per_trajectory=True).cpu().numpy()
+    err = np.abs(L - g['losses']).max()
+    print(f'simopt: engine vs reference evaluate_once, max abs err {err:.2e} over {L.size} (candidate, trajectory) pairs')
+    assert err <= 1e-9
+    np.testing.assert_allclose(obj.evaluate(g['candidates'][:, :2]).cpu().numpy(), g['losses'].mean(1), rtol=0, atol=1e-9)
+
+
+def test_engine_reproduces_reference_roll_out_golden():
+    """The golden rollout recorded from the UNMODIFIED reference's IWPGAlgorithm.roll_out (iwpg.py:350-385;
+    oracle/gen_golden_rollout.py) through the engine's pieces:
+      * float64 tape-mode env kernels on the recorded draws and the recorded actions give the observations and
+        rewards the reference's Buffer stored, incl. the first observation after every in-rollout reset (1e-6: the
+        Buffer holds float32);
+      * the policy kernels (CUDA-core float32 and tcgen05 split-TF32) on the stored observations give the stored
+        values (2e-5) and the Gaussian means behind the stored actions;
+      * pdx_gae on the stored rewards / values with roll_out's episode boundaries gives the stored advantages,
+        value targets and discounted returns (2e-4), reward scaling on."""
+    from phoenix_drone_simulation_b200 import VecEnv
+    from phoenix_drone_simulation_b200.rollout import ActorCritic, compute_gae
+    g = _load('rollout_hover_simple')
+    T, env_id = int(g['T']), str(g['env_id'])
+    dev = torch.device('cuda')
+    # ---- env
+    env = VecEnv(env_id, 2, dtype=torch.float64, rng='tape', keep_final_obs=True)
+    S, R = env.tape_slots['step'], env.tape_slots['reset']
+    col = lambda v, slots: torch.as_tensor(np.asarray(v[:slots], dtype=np.float64), device=dev)[:, None].repeat(1, 2).contiguous()
+    env.construct_from_tape(col(g['init_tape'], env.tape_slots['init']))
+    env.set_tapes(reset=col(g['reset_tape'][0], R))
+    o = env.reset()
+    np.testing.assert_allclose(o[0].cpu().numpy(), g['obs'][0], rtol=0, atol=1e-6)
+    reset_of_step = {int(t): e for e, t in enumerate(g['reset_after'])}
+    done = np.zeros(T, np.uint8)
+    for t in range(T):
+        e = reset_of_step.get(t)
+        env.set_tapes(step=col(g['step_tape'][t], S), reset=col(g['reset_tape'][e] if e is not None else np.zeros(R), R))
+        o, r, term, trunc, _ = env.step(torch.as_tensor(g['act'][t], device=dev).expand(2, 4).contiguous())
+        assert abs(float(r[0]) - float(g['rew'][t])) <= 1e-5 * max(1.0, abs(float(g['rew'][t])))
+        ended = bool(term[0] | trunc[0])
+        assert ended == (e is not None and t < T - 1) or t == T - 1
+        done[t] = 1 if bool(term[0]) else 0
+        if t + 1 < T:
+            np.testing.assert_allclose(o[0].cpu().numpy(), g['obs'][t + 1], rtol=0, atol=1e-6)
+    next_obs = o[0].float()[None].contiguous()               # the observation the epoch cut is bootstrapped from
+    # ---- policy
+    for kernel, tol in (('cuda', 2e-5), ('tc', 2e-5)):
+        ac = ActorCritic(env.obs_dim, policy_kernel=kernel)
+        sd = {k[3:]: torch.as_tensor(g[k]) for k in g if k.startswith('sd.')}
+        missing = ac.load_state_dict(sd, strict=False)
+        assert [k for k in missing.missing_keys if 'extra_state' not in k] == [] and missing.unexpected_keys == []
+        obs = torch.as_tensor(g['obs'], device=dev).contiguous()
+        act = torch.empty((T, 4), device=dev); val = torch.empty(T, device=dev); lp = torch.empty(T, device=dev); mu = torch.empty((T, 4), device=dev)
+        ac.step_into(obs, act, val, lp, mu)
+        np.testing.assert_allclose(val.cpu().numpy(), g['val'], rtol=tol, atol=tol)
+        eps = (torch.as_tensor(g['act'], device=dev) - mu) / torch.exp(ac.log_std)          # the reference's draws
+        lp_ref = (-0.5 * eps ** 2 - ac.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        np.testing.assert_allclose(lp_ref.cpu().numpy(), g['logp'], rtol=2e-4, atol=2e-4)
+        last_val = ac.value(next_obs)
+    # ---- GAE with roll_out's boundaries: terminated -> 0, epoch cut -> V(next obs)
+    c = lambda x: torch.as_tensor(np.asarray(x), device=dev)[:, None].contiguous()
+    adv, tv, dr = compute_gae(c(g['rew']), c(g['val']), c(done), torch.zeros((T, 1), device=dev), last_val, 0.99, 0.95,
+                              torch.as_tensor(g['sd.ret_oms.std'], device=dev))
+    np.testing.assert_allclose(adv[:, 0].cpu().numpy(), g['adv'], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(tv[:, 0].cpu().numpy(), g['target_v'], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(dr[:, 0].cpu().numpy(), g['discounted_ret'], rtol=2e-4, atol=2e-4)
