@@ -68,7 +68,9 @@ class TrajectoryObjective:
         self.act = torch.as_tensor(actions, dtype=torch.float32, device=device)
         self.pre = torch.as_tensor(pre_inputs, dtype=torch.float32, device=device)
         self.M, self.T = self.obs.shape[:2]
-        kw = dict(domain_randomization=-1, observation_noise=-1, auto_reset=False)     # pybullet.py:263-265
+        # pybullet.py:263-265; evaluate_once switches the reset distribution off for good (pybullet.py:157), so
+        # the pre-steps start from a drone at rest with motor state 0
+        kw = dict(domain_randomization=-1, observation_noise=-1, auto_reset=False, enable_reset_distribution=False)
         kw.update(env_kwargs)
         self.env_id, self.device, self.dtype, self.gamma, self.seed, self.kw = env_id, device, dtype, gamma, seed, kw
         self._env = None
