@@ -12,6 +12,13 @@ from .lib import PhoenixB200Error, LIB_PATH  # noqa: F401
 from .config import EnvConfig, ENV_IDS, MAX_EPISODE_STEPS  # noqa: F401
 
 
+try:                            # like the reference's __init__.py:8-50: importing the package registers the ids
+    import gymnasium as _gymnasium_present  # noqa: F401
+    from . import envs as _envs  # noqa: F401  (registers on import)
+except Exception:               # gymnasium is optional: the local make() below is the registry then
+    pass
+
+
 def __getattr__(name):          # torch-dependent modules are imported lazily
     if name in ('VecEnv',):
         from .vec_env import VecEnv

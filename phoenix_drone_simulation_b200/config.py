@@ -74,6 +74,10 @@ class EnvConfig:
     auto_reset: bool = True
     lin_damping: float = 0.04
     ang_damping: float = 0.04
+    # None = the agent's default (agents.py:165,196); the reference's debug scripts switch them off by assigning
+    # to drone.use_latency / drone.use_motor_dynamics after construction
+    use_latency: object = None
+    use_motor_dynamics: object = None
     render_mode: object = None
     debug: bool = False
     extra: dict = field(default_factory=dict)
@@ -109,8 +113,12 @@ class EnvConfig:
         c.obs_rate = int(self.sim_freq // self.observation_frequency)           # base.py:108
         time_step = 1. / self.sim_freq                                          # base.py:98
         c.use_latency = 1 if (bullet and self.latency >= time_step) else 0      # agents.py:165
+        if self.use_latency is not None and bullet:
+            c.use_latency = 1 if (self.use_latency and self.latency >= time_step) else 0
         c.buf_size = int(max(1, int(self.latency // time_step)))                # agents.py:180
         c.use_motor_dynamics = 1 if bullet else 0
+        if self.use_motor_dynamics is not None and bullet:
+            c.use_motor_dynamics = 1 if self.use_motor_dynamics else 0
         c.reset_distribution = 1 if self.enable_reset_distribution else 0
         c.ground_effect = 1 if self.use_ground_effect else 0
         c.max_episode_steps = int(self.max_episode_steps)

@@ -195,3 +195,18 @@ def test_flag_constants_match_the_header():
     assert defs['PDX_POLICY_TC_OVERLAP'] == L.PDX_POLICY_TC_OVERLAP
     assert 'flags' in [f[0] for f in L.PdxBuffers._fields_] and 'int32_t flags;' in header
     assert L.PDX_POLICY_TC_OVERLAP & 3 == 0          # must not collide with the precision values 1 and 3
+
+
+def test_ids_are_registered_on_import():
+    """phoenix_drone_simulation/__init__.py:8-50: importing the package registers the six ids with gymnasium when it
+    is installed; the local make() is the registry otherwise."""
+    import phoenix_drone_simulation_b200 as pds
+    from phoenix_drone_simulation_b200 import envs
+    assert set(envs.registry) == set(pds.ENV_IDS)
+    try:
+        import gymnasium
+    except ImportError:
+        assert envs.register_with_gymnasium() is False
+        return
+    for env_id in pds.ENV_IDS:
+        assert env_id in gymnasium.envs.registry
