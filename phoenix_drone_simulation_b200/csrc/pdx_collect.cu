@@ -42,7 +42,6 @@ struct CollectArgs {
   const float* mean; const float* std; float eps;
   const float* log_std;
   const float* packed;                       // weight image of pdx_policy_tc_pack (same precision)
-  const float* pi_b[2]; const float* v_b[2]; // hidden-layer biases (added in the epilogues)
   int32_t pi_h[2], v_h[2];
   uint64_t pol_seed, pol_counter;
   float* act; float* val; float* logp;       // [T][n][4], [T][n], [T][n]
@@ -59,19 +58,18 @@ struct ColCfg {
   static constexpr uint32_t kR0 = 0, kR1 = 128, kR2 = 256;
 };
 
-__host__ __device__ inline int64_t collect_w_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words; }   // B1, B2a, B2c of one image
+__host__ __device__ inline int64_t collect_w_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kColBiasWords; }   // B1, B2a, B2c, Bc of one image
 
 // shared-memory plan (bytes), in this order
 struct ColSmem {
-  size_t ctrl, norm, bias, common, weights, x, tiles, moments, total;
+  size_t ctrl, norm, common, weights, x, tiles, moments, total;
 };
 template <bool X3>
 __host__ __device__ inline ColSmem collect_smem(int k1, int D, int warps) {
   ColSmem s;
   s.ctrl = 0;                                          // 256 bytes of barriers / slot bookkeeping
   s.norm = 256;
-  s.bias = s.norm + (size_t)k1 * 8;
-  s.common = s.bias + 256 * 4;                         // b1[128], b2[128]
+  s.common = s.norm + (size_t)k1 * 8;
   s.common = (s.common + 15) & ~(size_t)15;
   s.weights = s.common + (size_t)kCommonWords * 4;
   s.x = s.weights + (size_t)ColCfg<X3>::kImages * collect_w_words(k1) * 4;
@@ -126,8 +124,6 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   uint32_t* tile_info = reinterpret_cast<uint32_t*>(smem + 96);    // [4] slot | parity << 8 of the tile's current policy step
   float* act_std = reinterpret_cast<float*>(smem + 128);           // exp(log_std)[4], log_std[4]
   float2* norm = reinterpret_cast<float2*>(smem + sp.norm);        // [K1] (mean, 1 / (std + eps))
-  float* bias1 = reinterpret_cast<float*>(smem + sp.bias);         // [128] actor | critic, layer 1
-  float* bias2 = bias1 + 128;                                      // [128] layer 2
   float* common = reinterpret_cast<float*>(smem + sp.common);      // w3a[64][4], w3c[64], b3[16]
   float* bw = reinterpret_cast<float*>(smem + sp.weights);         // B1, B2a, B2c (hi) [, the same (lo)]
   unsigned char* xbuf = smem + sp.x;
@@ -157,19 +153,15 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
     if (k < D && p.std) { mu = p.mean[k]; inv = 1.0f / (p.std[k] + p.eps); }
     norm[k] = make_float2(mu, inv);
   }
-  for (int k = tid; k < 128; k += B) {
-    const int j = k & 63;
-    const bool critic = k >= 64;
-    bias1[k] = j < (critic ? p.v_h[0] : p.pi_h[0]) ? (critic ? p.v_b[0] : p.pi_b[0])[j] : 0.0f;
-    bias2[k] = j < (critic ? p.v_h[1] : p.pi_h[1]) ? (critic ? p.v_b[1] : p.pi_b[1])[j] : 0.0f;
-  }
   // K padding chunks of the operand buffers: zero, once
   {
     const int n_chunks = (D + 3) >> 2;
     for (int e = tid; e < Cfg::kSlots * Cfg::kImages * kTile * (K1 / 4 - n_chunks); e += B) {
       const int m = e & (kTile - 1), r = e >> 7;
       const int kc = n_chunks + r % (K1 / 4 - n_chunks), img = r / (K1 / 4 - n_chunks);
-      *reinterpret_cast<float4*>(xbuf + (size_t)img * (K1 / 4) * kLboA + kc * kLboA + m * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+      // (img: slot-major, hi image first; the constant-1 column D starts a padding chunk when D is a multiple of 4)
+      const float one = (4 * kc == D && (!X3 || (img & 1) == 0)) ? 1.0f : 0.0f;
+      *reinterpret_cast<float4*>(xbuf + (size_t)img * (K1 / 4) * kLboA + kc * kLboA + m * 16) = make_float4(one, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
@@ -205,6 +197,8 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   T* state = reinterpret_cast<T*>(a.b.state);
   T* my_row = tile0 + (size_t)tid * D;
   const int row = 32 * wq + lane;                              // this thread's row of the tile = its TMEM lane
+  // layer-2 biases ride on a constant-1 hidden unit after the actor's last one (the pack put a 1 into row D of B1
+  // there, the actor's bias into that unit's row of B2a and the critic's into Bc): pi_h[0] < 64 is required
   const int EPC = B;                                           // environments per CTA and pass
 
   for (int64_t g = blockIdx.x; g < p.groups; g += gridDim.x) {
@@ -258,8 +252,8 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = 4 * kc + j;
-          float x = 0.0f;
-          if (k < D) { const float2 nm = norm[k]; x = valid ? (my_row[k] - nm.x) * nm.y : 0.0f; }
+          float x = k == D ? 1.0f : 0.0f;                       // column D: constant 1 (row D of B1 = the layer-1 biases)
+          if (k < D) { const float2 nm = norm[k]; x = (my_row[k] - nm.x) * nm.y; }
           hi[j] = tf32_rna(x);
           lo[j] = x - __uint_as_float(hi[j]);
         }
@@ -307,16 +301,11 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         tmem_ld16(taddr + R0 + 16 * ch, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias1 + 16 * ch + 4 * j4);
-          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = __uint_as_float(r[4 * j4 + j]) + bv[j];
-            const float y = ch < 4 ? fmaxf(x, 0.0f) : (X3 ? tanh_fast(x) : tanh_mufu(x));
-            r[4 * j4 + j] = tf32_rna(y);
-            lo[4 * j4 + j] = __float_as_uint(y - __uint_as_float(r[4 * j4 + j]));
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float x = __uint_as_float(r[j]);                // (the bias came in through the constant-1 column of X)
+          const float y = ch < 4 ? fmaxf(x, 0.0f) : (X3 ? tanh_fast(x) : tanh_mufu(x));
+          r[j] = tf32_rna(y);
+          lo[j] = __float_as_uint(y - __uint_as_float(r[j]));
         }
         tmem_st16(taddr + R0 + 16 * ch, r);
         if (X3) tmem_st16(taddr + R2 + 16 * ch, lo);
@@ -348,6 +337,11 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
           }
           a_hi += 8; a_lo += 8; bha += kstep; bhc += kstep; bla += kstep; blc += kstep;
         }
+        {                                                      // critic bias: the actor's constant-1 unit times Bc
+          const uint32_t off = (uint32_t)(p.pi_h[0] & ~7);
+          if (X3) mma_ts(tcol + R1 + 64, tcol + R0 + off, blc, idesc, 1);     // (the unit's lo part is 0)
+          mma_ts(tcol + R1 + 64, tcol + R0 + off, bhc, idesc, 1);
+        }
         tc_commit(bar2);
       }
       mbar_wait(bar2, par);
@@ -363,14 +357,14 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         if (ch < 4) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float y = fmaxf(__uint_as_float(r[j]) + bias2[16 * ch + j], 0.0f);
+            const float y = fmaxf(__uint_as_float(r[j]), 0.0f);
             const float4 wv = *reinterpret_cast<const float4*>(w3a + 4 * (16 * ch + j));
             mu[0] = fmaf(y, wv.x, mu[0]); mu[1] = fmaf(y, wv.y, mu[1]); mu[2] = fmaf(y, wv.z, mu[2]); mu[3] = fmaf(y, wv.w, mu[3]);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float x = __uint_as_float(r[j]) + bias2[16 * ch + j];
+            const float x = __uint_as_float(r[j]);
             const float y = X3 ? tanh_fast(x) : tanh_mufu(x);
             v = fmaf(y, w3c[16 * (ch - 4) + j], v);
           }
@@ -404,15 +398,28 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
       if (p.obs_moments) {                                      // (the slot is free again: off the tiles' critical path)
         const int rows_w = (int)max((int64_t)0, min((int64_t)32, n - (i - lane)));
         const T* wrow = my_row - lane * D;
+        // float32 sums about the warp's own first row (tiny differences for a nearly constant column: no
+        // cancellation), moved to the common shift in float64.  Columns 0..31: one lane each over the warp's
+        // rows; columns 32..D-1 (two for the 34-wide hover row): nc lanes x G row groups, folded by shuffles
+        const int nc = D > 32 ? D - 32 : 0;
+        int G = 1;
+        while (nc && 2 * G * nc <= 32) G *= 2;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int col = lane + 32 * h;
-          if (col < D && rows_w > 0) {
-            // float32 sums about the warp's own first row (tiny differences for a nearly constant column: no
-            // cancellation), moved to the common shift in float64
-            const float cw = wrow[col];
-            float s1 = 0.0f, s2 = 0.0f;
-            for (int r = 1; r < rows_w; ++r) { const float d = wrow[r * D + col] - cw; s1 += d; s2 = fmaf(d, d, s2); }
+          if (h == 1 && nc == 0) break;
+          const int g = h ? lane / nc : 0, col = h ? 32 + lane % nc : lane, stride = h ? G : 1;
+          const bool on = h ? g < G : col < D;
+          float cw = 0.0f, s1 = 0.0f, s2 = 0.0f;
+          if (on && rows_w > 0) {
+            cw = wrow[col];
+            for (int r = h ? g : 1; r < rows_w; r += stride) { const float d = wrow[r * D + col] - cw; s1 += d; s2 = fmaf(d, d, s2); }
+          }
+          if (h)
+            for (int sft = G >> 1; sft; sft >>= 1) {
+              s1 += __shfl_down_sync(0xffffffffu, s1, sft * nc);
+              s2 += __shfl_down_sync(0xffffffffu, s2, sft * nc);
+            }
+          if (on && g == 0 && rows_w > 0) {
             const double dc = (double)cw - (double)norm[col].x, nr = (double)rows_w;
             mom[col] += (double)s1 + nr * dc;
             mom[64 + col] += (double)s2 + 2.0 * dc * (double)s1 + nr * dc * dc;
@@ -494,9 +501,9 @@ extern "C" int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const Pd
   if (pol->obs_dim != c.obs_dim || (pol->precision != 1 && pol->precision != 3) || !pol->pi || !pol->v || !pol->log_std || !pol->packed)
     return set_error(PDX_ERR_INVALID, "pdx_collect: bad policy description");
   const PdxMlp* pi = pol->pi; const PdxMlp* v = pol->v;
-  if (pi->hidden[0] < 1 || pi->hidden[0] > 64 || pi->hidden[1] < 1 || pi->hidden[1] > 64 || pi->n_out < 1 || pi->n_out > 4 ||
+  if (pi->hidden[0] < 1 || pi->hidden[0] > 63 || pi->hidden[1] < 1 || pi->hidden[1] > 64 || pi->n_out < 1 || pi->n_out > 4 ||
       v->hidden[0] < 1 || v->hidden[0] > 64 || v->hidden[1] < 1 || v->hidden[1] > 64 || v->n_out != 1)
-    return set_error(PDX_ERR_INVALID, "pdx_collect: networks must have two hidden layers of <= 64 units (actor <= 4 outputs, critic 1)");
+    return set_error(PDX_ERR_INVALID, "pdx_collect: networks must have two hidden layers of <= 64 units (actor: first layer <= 63, <= 4 outputs; critic: 1 output)");
   if (out->n_steps < 1 || out->n_steps > (1 << 20) || !out->obs0 || !out->act || !out->val || !out->logp || !out->last_val)
     return set_error(PDX_ERR_INVALID, "pdx_collect: n_steps must be in [1, 2^20] and obs0 / act / val / logp / last_val are required");
   if (!out->scratch || out->scratch_bytes < pdx_collect_scratch_bytes(buf->device))
@@ -515,9 +522,9 @@ extern "C" int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const Pd
   ka.dump_step = ka.dump_reset = ka.dump_init = nullptr;
   ka.n_steps = out->n_steps; ka.n_tiles = 1;
   CollectArgs p;
-  p.obs_dim = c.obs_dim; p.k1 = (c.obs_dim + 7) & ~7; p.act_dim = pi->n_out; p.n_steps = out->n_steps;
+  p.obs_dim = c.obs_dim; p.k1 = tc_k1(c.obs_dim); p.act_dim = pi->n_out; p.n_steps = out->n_steps;
   p.obs0 = out->obs0; p.mean = pol->mean; p.std = pol->std; p.eps = pol->eps; p.log_std = pol->log_std; p.packed = pol->packed;
-  for (int k = 0; k < 2; ++k) { p.pi_b[k] = pi->bias[k]; p.v_b[k] = v->bias[k]; p.pi_h[k] = pi->hidden[k]; p.v_h[k] = v->hidden[k]; }
+  for (int k = 0; k < 2; ++k) { p.pi_h[k] = pi->hidden[k]; p.v_h[k] = v->hidden[k]; }
   p.pol_seed = pol->seed; p.pol_counter = pol->counter;
   p.act = out->act; p.val = out->val; p.logp = out->logp; p.last_val = out->last_val;
   p.scratch = reinterpret_cast<unsigned char*>(out->scratch);

@@ -63,7 +63,7 @@ struct TcArgs {
 // ---------------------------------------------------------------------------------------------
 //  Packed weight image (global == shared layout), floats:
 //    common  w3a[64][4] (actor output weights, [hidden][action]), w3c[64] (critic), b3[16] (mu biases 0..3, v bias 4)
-//    Bhi     B1[K1/4][128][4]  B2a[16][64][4]  B2c[16][64][4]
+//    Bhi     B1[K1/4][128][4]  B2a[16][64][4]  B2c[16][64][4]  Bc[2][64][4] (pdx_collect's critic layer-2 bias tile)
 //            bias tiles  Bb1[2][128][4]  Bb2a[2][64][4]  Bb2c[2][64][4]                  (tf32-rounded)
 //    Blo     same shapes, w - hi                                                  (precision 3 only)
 //  B?[kc][n][j] = W[n][4 kc + j]  (torch nn.Linear weight is [out][in]): exactly the no-swizzle K-major
@@ -101,6 +101,11 @@ __global__ void k_pack_tc(const PackArgs a) {
       if (k < D) {
         if (n < 64) { if (n < a.pi_h1) w = a.pi_w[0][n * D + k]; }
         else if (n - 64 < a.v_h1) w = a.v_w[0][(n - 64) * D + k];
+      } else if (k == D) {                                // the constant-1 column of X (pdx_collect): layer-1 biases, and
+        if (n < 64) {                                     // a constant-1 hidden unit after the actor's last one
+          if (n < a.pi_h1) w = a.pi_b[0][n];
+          else if (n == a.pi_h1) w = 1.0f;
+        } else if (n - 64 < a.v_h1) w = a.v_b[0][n - 64];
       }
     } else if ((r -= K1 * kN1) < 2 * kB2Words) {          // B2a, B2c: N = 64, K = 64
       const bool critic = r >= kB2Words;
@@ -108,8 +113,12 @@ __global__ void k_pack_tc(const PackArgs a) {
       const int kc = r / 256, n = (r / 4) % 64, k = 4 * kc + (r & 3);
       const int h1 = critic ? a.v_h1 : a.pi_h1, h2 = critic ? a.v_h2 : a.pi_h2;
       if (n < h2 && k < h1) w = (critic ? a.v_w[1] : a.pi_w[1])[n * h1 + k];
+      else if (!critic && n < h2 && k == h1) w = a.pi_b[1][n];      // (h1 < 64) the constant-1 unit's row: actor layer-2 bias
+    } else if ((r -= 2 * kB2Words) < kColBiasWords) {     // pdx_collect: extra K step of the critic's layer 2 over the
+      const int kc = r / 256, n = (r / 4) % 64, k = 4 * kc + (r & 3);   // actor columns 8 (pi_h1 / 8) ..: constant-1 unit
+      if (a.pi_h1 < 64 && k == (a.pi_h1 & 7) && n < a.v_h2) w = a.v_b[1][n];
     } else {                                              // bias tiles: only element (kc = 0, n, j = 0) is non-zero
-      r -= 2 * kB2Words;
+      r -= kColBiasWords;
       if (r < 8 * kN1) {
         const int n = r / 4;
         if ((r & 3) == 0 && n < kN1) { if (n < 64) { if (n < a.pi_h1) w = a.pi_b[0][n]; } else if (n - 64 < a.v_h1) w = a.v_b[0][n - 64]; }
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(TcCfg<X3>::kThreads + 32, TcCfg<X3>::kMinBlock
     //  warp-uniform values; the wrappers elect the lane that executes the instruction.
     // =====================================================================================
     const uint32_t b1_s = smem_u32(bhi), b2a_s = b1_s + K1 * kN1 * 4, b2c_s = b2a_s + kB2Words * 4;
-    const uint32_t bb1_s = b2c_s + kB2Words * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4;
+    const uint32_t bb1_s = b2c_s + (kB2Words + kColBiasWords) * 4, bb2a_s = bb1_s + 8 * kN1 * 4, bb2c_s = bb2a_s + 8 * 64 * 4;
     const uint32_t lo_off = (uint32_t)bwords * 4;          // Blo = Bhi + lo_off (bytes)
     const uint32_t a1hi_s = smem_u32(a1hi), a1lo_s = smem_u32(a1lo);
     const uint64_t ones_desc = make_desc(smem_u32(ones), 2048, kSbo);
@@ -569,7 +578,7 @@ bool tc_shapes_ok(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t pr
   if (obs_dim <= 0 || !pi || !v || (precision != 1 && precision != 3)) return false;
   if (pi->hidden[0] < 1 || pi->hidden[0] > 64 || pi->hidden[1] < 1 || pi->hidden[1] > 64 || pi->n_out < 1 || pi->n_out > 4) return false;
   if (v->hidden[0] < 1 || v->hidden[0] > 64 || v->hidden[1] < 1 || v->hidden[1] > 64 || v->n_out != 1) return false;
-  const int k1 = (obs_dim + 7) & ~7;
+  const int k1 = tc_k1(obs_dim);
   if (k1 > 64) return false;                              // sixteen lanes walk the K chunks of a row (stage_to_x)
   return tc_smem_bytes(k1, obs_dim, precision == 3) <= (size_t)227 * 1024;
 }
@@ -585,7 +594,7 @@ extern "C" int pdx_policy_tc_timing(long long* out) {
 extern "C" int64_t pdx_policy_tc_pack_words(int32_t obs_dim, const PdxMlp* pi, const PdxMlp* v, int32_t precision) {
   if (!tc_shapes_ok(obs_dim, pi, v, precision))
     return pdx::set_error(PDX_ERR_INVALID, "tensor-core policy plan: needs two hidden layers <= 64, n_out <= 4, obs_dim <= 64, precision 1 or 3");
-  const int k1 = (obs_dim + 7) & ~7;
+  const int k1 = tc_k1(obs_dim);
   return kCommonWords + (precision == 3 ? 2 : 1) * tc_b_words(k1);
 }
 
@@ -595,7 +604,7 @@ extern "C" int pdx_policy_tc_pack(int32_t obs_dim, const PdxMlp* pi, const PdxMl
   const int rc = tc_select_device_of(packed);
   if (rc) return rc;
   PackArgs p;
-  p.obs_dim = obs_dim; p.k1 = (obs_dim + 7) & ~7; p.x3 = precision == 3;
+  p.obs_dim = obs_dim; p.k1 = tc_k1(obs_dim); p.x3 = precision == 3;
   p.pi_h1 = pi->hidden[0]; p.pi_h2 = pi->hidden[1]; p.v_h1 = v->hidden[0]; p.v_h2 = v->hidden[1]; p.act_dim = pi->n_out;
   for (int k = 0; k < 3; ++k) { p.pi_w[k] = pi->weight[k]; p.pi_b[k] = pi->bias[k]; p.v_w[k] = v->weight[k]; p.v_b[k] = v->bias[k]; }
   p.out = packed;
@@ -615,7 +624,7 @@ extern "C" int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, 
   if (rc) return rc;
   const bool x3 = precision == 3;
   TcArgs a;
-  a.n = n; a.obs_dim = obs_dim; a.k1 = (obs_dim + 7) & ~7; a.act_dim = pi->n_out;
+  a.n = n; a.obs_dim = obs_dim; a.k1 = tc_k1(obs_dim); a.act_dim = pi->n_out;
   a.flags = overlap;
   a.obs = obs; a.mean = mean; a.std = std; a.eps = eps; a.log_std = log_std; a.packed = packed;
   a.seed = seed; a.counter = counter; a.env_offset = env_offset; a.act = actions; a.val = values; a.logp = logp; a.mu = mu_out;

@@ -163,7 +163,14 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, r, 1.0f);
 }
 
-// floats of one operand image (hi or lo): B1[K1/4][128][4], B2a[16][64][4], B2c[16][64][4], bias tiles
-__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kBiasTileWords; }
+// K of layer 1: the observation columns, ONE constant-1 column (column D: row D of B1 carries the layer-1 biases, so
+// the fused collector needs no bias pass; k_policy_tc keeps that column at 0 and uses its bias tiles), zero padding to
+// a multiple of the tf32 MMA K (8).  Rows that are a multiple of 16 wide get no such column: pdx_collect does not take
+// them (its bulk-copy rule), and for k_policy_tc alone the extra K step would be wasted shared memory
+__host__ __device__ inline int tc_k1(int obs_dim) { return (obs_dim & 15) == 0 ? obs_dim : (obs_dim + 8) & ~7; }
+constexpr int kColBiasWords = 8 * 64;                   // K = 8 tile of the collector: row (pi_h1 & 7) = critic layer-2 bias
+
+// floats of one operand image (hi or lo): B1[K1/4][128][4], B2a[16][64][4], B2c[16][64][4], collector bias tile, bias tiles
+__host__ __device__ inline int64_t tc_b_words(int k1) { return (int64_t)k1 * kN1 + 2 * kB2Words + kColBiasWords + kBiasTileWords; }
 
 }  // namespace

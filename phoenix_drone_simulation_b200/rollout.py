@@ -519,6 +519,8 @@ class RolloutCollector:
         p = lambda t: t.data_ptr() if t is not None else None
         stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
         pi, v = ac._mlp_struct(ac.pi, ac.log_std.shape[0]), ac._mlp_struct(ac.v, 1)
+        if pi.hidden[0] > 63:                       # the kernel needs room for a constant-1 unit after the actor's first layer
+            return False
         pack = ac._packed_weights(env.obs_dim, pi, v, stream)
         if ac.tc_precision not in (1, 3):          # the shapes fell outside the tensor-core plan while packing
             return False

@@ -167,12 +167,14 @@ def test_tensor_core_policy_shape_checks_need_no_device(lib):
         m.hidden[0], m.hidden[1], m.n_out = h1, h2, n_out
         return m
     pi, v = mlp(50, 50, 4), mlp(64, 64, 1)
-    k1 = 40                                            # obs_dim 34 padded to a multiple of 8
-    b_words = k1 * 128 + 2 * 64 * 64 + 8 * (128 + 64 + 64)
+    k1 = 40                                            # obs_dim 34 + the constant-1 column, padded to a multiple of 8
+    b_words = k1 * 128 + 2 * 64 * 64 + 8 * 64 + 8 * (128 + 64 + 64)      # B1, B2a, B2c, collector bias tile, bias tiles
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(v), 1) == 336 + b_words
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(v), 3) == 336 + 2 * b_words
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(v), 2) == -1          # precision is 1 or 3
     assert lib.pdx_policy_tc_pack_words(160, C.byref(pi), C.byref(v), 3) == -1         # too wide
+    assert lib.pdx_policy_tc_pack_words(40, C.byref(pi), C.byref(v), 1) == 336 + b_words + 8 * 128    # 40 -> K = 48
+    assert lib.pdx_policy_tc_pack_words(48, C.byref(pi), C.byref(v), 1) == 336 + b_words + 8 * 128    # 48 -> K = 48
     assert lib.pdx_policy_tc_pack_words(34, C.byref(mlp(65, 50, 4)), C.byref(v), 3) == -1
     assert lib.pdx_policy_tc_pack_words(34, C.byref(pi), C.byref(mlp(64, 64, 2)), 3) == -1
     assert lib.pdx_policy_step_tc(0, 34, None, None, None, 0.0, C.byref(pi), C.byref(v), None, None, 3, 0, 0, 0,
