@@ -33,6 +33,17 @@
 #include "pdx_tc.cuh"
 #include "pdx_error.h"
 
+#ifndef PDX_COL_LEADER_WAIT
+// Tuning hooks (tools/build_variant.sh, tools/ab_collect.sh).  Both "lighter" synchronisations measured SLOWER on
+// configs[4] (1408 us with the barriers, 1419 us with leader-only waits, 1455 us with the counter release): the
+// barriers keep the four warps of a tile on the same instructions, and the loop body (159 KB of SASS) lives or dies
+// by instruction-cache sharing.
+#define PDX_COL_LEADER_WAIT 0        // 1 = only the issuing warp waits at the hand-off barriers, the others arrive
+#endif
+#ifndef PDX_COL_COUNTER_RELEASE
+#define PDX_COL_COUNTER_RELEASE 0    // 1 = the tile's last warp out of the layer-2 epilogue releases the slot (no barrier)
+#endif
+
 namespace pdx {
 
 struct CollectArgs {
@@ -122,6 +133,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   uint32_t* slot_busy = reinterpret_cast<uint32_t*>(smem + 72);    // [kSlots]
   uint32_t* slot_phase = reinterpret_cast<uint32_t*>(smem + 80);   // [kSlots] parity of the slot's two mbarriers
   uint32_t* tile_info = reinterpret_cast<uint32_t*>(smem + 96);    // [4] slot | parity << 8 of the tile's current policy step
+  uint32_t* tile_done = reinterpret_cast<uint32_t*>(smem + 112);   // [4] warps of the tile that are through with the slot
   float* act_std = reinterpret_cast<float*>(smem + 128);           // exp(log_std)[4], log_std[4]
   float2* norm = reinterpret_cast<float2*>(smem + sp.norm);        // [K1] (mean, 1 / (std + eps))
   float* common = reinterpret_cast<float*>(smem + sp.common);      // w3a[64][4], w3c[64], b3[16]
@@ -142,6 +154,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
     for (int s = 0; s < 2 * Cfg::kSlots; ++s) mbar_init(bar_w + 8 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < Cfg::kSlots; ++s) { slot_busy[s] = 0; slot_phase[s] = 0; }
+    for (int s = 0; s < 4; ++s) tile_done[s] = 0;
   }
   if (tid < 4) {
     const float ls = tid < p.act_dim ? p.log_std[tid] : 0.0f;
@@ -246,7 +259,23 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
       unsigned char* xl = xh + (size_t)(K1 / 4) * kLboA;
       tc_fence_after();
       // ---- X: this thread's standardised row in the canonical K-major layout (row m, K chunk kc at kc * LBO + m * 16)
-      for (int kc = 0; kc < ((D + 3) >> 2); ++kc) {
+      // (rows of environments past the end of the shard hold whatever the tile held: rows are independent)
+#pragma unroll 3
+      for (int kc = 0; kc < (D >> 2); ++kc) {                  // whole chunks
+        uint32_t hi[4];
+        float lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 nm = norm[4 * kc + j];
+          const float x = (my_row[4 * kc + j] - nm.x) * nm.y;
+          hi[j] = tf32_rna(x);
+          lo[j] = x - __uint_as_float(hi[j]);
+        }
+        *reinterpret_cast<uint4*>(xh + kc * kLboA + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (X3) *reinterpret_cast<float4*>(xl + kc * kLboA + row * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      if (D & 3) {                                             // the last chunk: data, the constant-1 column D, zeros
+        const int kc = D >> 2;
         uint32_t hi[4];
         float lo[4];
 #pragma unroll
@@ -261,7 +290,8 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         if (X3) *reinterpret_cast<float4*>(xl + kc * kLboA + row * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_async_smem();                                      // generic-proxy writes of X -> visible to the tensor core
-      named_bar_sync(bar_id, tile_threads);
+      // only the issuing warp waits for the tile's rows; the others go on to their Gaussian draws
+      if (leader_warp || !PDX_COL_LEADER_WAIT) named_bar_sync(bar_id, tile_threads); else named_bar_arrive(bar_id, tile_threads);
       // ---- layer 1: D1[128 x 128] = X . B1 (columns 0..63 actor, 64..127 critic)
       if (leader_warp) {
         constexpr uint32_t idesc = make_idesc(kN1);
@@ -312,7 +342,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
       }
       tmem_wait_st();
       tc_fence_before();
-      named_bar_sync(bar_id, tile_threads);
+      if (leader_warp || !PDX_COL_LEADER_WAIT) named_bar_sync(bar_id, tile_threads); else named_bar_arrive(bar_id, tile_threads);
       // ---- layer 2: D2[:, 0:64] = a2[:, 0:64] . B2a, D2[:, 64:128] = a2[:, 64:128] . B2c (A from TMEM)
       if (leader_warp) {
         tc_fence_after();
@@ -371,8 +401,16 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         }
       }
       tc_fence_before();
-      named_bar_sync(bar_id, tile_threads);                    // every thread of the tile has read its D2 row
-      if (leader_warp && lane == 0) {                          // give the slot back
+#if !PDX_COL_COUNTER_RELEASE
+      named_bar_sync(bar_id, tile_threads);
+      if (leader_warp && lane == 0) {
+#else
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&tile_done[tile], 1u) == (uint32_t)tile_warps - 1u) {
+#endif
+        // the tile's last warp to have read its D2 rows gives the slot back (no barrier: the others are on their way
+        // into env.step)
+        tile_done[tile] = 0u;
         slot_phase[slot] = par ^ 1u;
         __threadfence_block();
         atomicExch(&slot_busy[slot], 0u);

@@ -7,7 +7,7 @@ name=$1; unit=$2; shift 2
 here=$(cd "$(dirname "$0")/.." && pwd)
 pkg=$here/phoenix_drone_simulation_b200
 extra=""
-case $unit in *f32*) extra="-use_fast_math";; *f64*) extra="-fmad=false";; esac
+case $unit in *f32*|pdx_collect.cu) extra="-use_fast_math";; *f64*) extra="-fmad=false";; esac
 obj=$pkg/build/variant_${name}_${unit%.cu}.o
 nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC $extra "$@" -c $pkg/csrc/$unit -o $obj
 objs=""
