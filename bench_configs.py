@@ -150,6 +150,11 @@ def main():
     if a.only:
         lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 3, k)))
                                         for k in a.kernels.split(',')],
+                 'configs[2] H=8': lambda: emit(dict(config='configs[2] H=8', **open_loop(
+                     'DroneCircleSimpleEnv-v0', sc(524288), 8, a.steps, a.warmup, uniform_actions, observation_history_size=8))),
+                 'configs[3]': lambda: emit(dict(config='configs[3]', **open_loop(
+                     'DroneTakeOffSimpleEnv-v0', sc(1048576), 8, a.steps, a.warmup, takeoff_actions, use_ground_effect=True,
+                     reset_on_nonfinite=True))),
                  'training': lambda: emit(dict(config='BASELINE.md PPO training FPS', **ppo_training(sc(16384), 64, 6)))}
         for name, fn in lines.items():
             if a.only in name:

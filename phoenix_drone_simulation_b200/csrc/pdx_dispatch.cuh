@@ -67,7 +67,7 @@ static void fill_devcfg(const PdxConfig& p, DevCfg<T>& d) {
 // ties go to double buffering, then to the larger block.
 struct LaunchShape { int block, tiles; size_t smem; };
 template <class T>
-static LaunchShape pick_shape(int D, int E) {
+static LaunchShape pick_shape(int D, int E, int wmode) {
   int forced = 0;
   if (const char* e = getenv("PDX_BLOCK")) {          // tuning hook: 32 / 64 / 128 / 256
     const int b = atoi(e);
@@ -79,7 +79,7 @@ static LaunchShape pick_shape(int D, int E) {
   for (int bi = 0; bi < 3; ++bi) {
     const int block = forced ? forced : blocks[bi];
     for (int tiles = 2; tiles >= 1; --tiles) {
-      const size_t smem = rollout_smem_bytes<T>(block, D, tiles, E);
+      const size_t smem = rollout_smem_bytes<T>(block, D, tiles, E, wmode);
       if (smem > (size_t)227 * 1024) continue;
       const int by_smem = (int)(((size_t)228 * 1024) / (smem + 1024));
       const int by_regs = 65536 / (128 * block);
@@ -101,15 +101,26 @@ static cudaError_t launch_kind(int kind, const KArgs<T>& ka, cudaStream_t st) {
     else k_reset<T, TASK, PHYS, NOISE, RNG, PID><<<grid, block, 0, st>>>(ka);
     return cudaGetLastError();
   }
-  const LaunchShape shape = pick_shape<T>(ka.c.obs_dim, ka.c.core_dim + 4);
+  // row mode of the observation tiles (rollout_smem_bytes): 2 = padded rows, 128-bit history shift -- float32 rows of
+  // whole 16-byte entries (Circle / TakeOff; measured: TakeOff H = 2 12.1 -> 14.4 G, Circle H = 8 2.75 -> 5.68 G
+  // env-steps/s); 1 = rotated walk for the other D % 16 == 0
+  typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
+  constexpr bool quad_ok = sizeof(T) == 4 && Mo::E % 4 == 0 && Mo::C % 4 == 0;
+  int wmode = (ka.c.obs_dim & 15) == 0 ? (quad_ok ? 2 : 1) : 0;
+  if (const char* e = getenv("PDX_WMODE")) {          // tuning hook: force mode 1 or 2 where legal
+    const int wv = atoi(e);
+    if (wmode && (wv == 1 || (wv == 2 && quad_ok))) wmode = wv;
+  }
+  const LaunchShape shape = pick_shape<T>(ka.c.obs_dim, ka.c.core_dim + 4, wmode);
   if (shape.block == 0) return cudaErrorInvalidConfiguration;
   const int block = shape.block;
   const size_t smem = shape.smem;
   KArgs<T> kb = ka;
   kb.n_tiles = shape.tiles;
-  const bool wide = (ka.c.obs_dim & 15) == 0;
-  auto kern = wide ? k_rollout<T, TASK, PHYS, NOISE, RNG, PID, true> : k_rollout<T, TASK, PHYS, NOISE, RNG, PID, false>;
-  static size_t smem_set[2][16] = {};               // per variant and device: opt-in dynamic shared memory
+  const int wide = wmode;
+  auto kern = wmode == 1 ? k_rollout<T, TASK, PHYS, NOISE, RNG, PID, 1> : k_rollout<T, TASK, PHYS, NOISE, RNG, PID, 0>;
+  if constexpr (quad_ok) { if (wmode == 2) kern = k_rollout<T, TASK, PHYS, NOISE, RNG, PID, 2>; }
+  static size_t smem_set[3][16] = {};               // per variant and device: opt-in dynamic shared memory
   const int dev = ka.b.device & 15;
   if (smem > smem_set[wide][dev]) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -587,10 +587,18 @@ __device__ __forceinline__ void fence_async_smem() {
 //   T stage [W][E][32]           only when D is a multiple of 16: column-major staging of the new entry
 //   T acc_ext [4][B], double acc_sum [4][B]   per-thread episode statistics (min/max ret, min/max len;
 //                                n, sum ret, sum ret^2, sum len), reduced once per launch
+//   Row modes (template parameter WIDE of the kernel):
+//     0  rows as in the output, walked word by word                (D not a multiple of 16)
+//     1  same layout, every lane walks its row rotated by its lane id, the new entry goes through `stage`
+//     2  rows padded by 16 bytes (an odd number of 16-byte vectors per row: 128-bit accesses of a quarter warp fall
+//        into eight different bank groups), history shifted with 128-bit loads / stores, every lane sends its own
+//        row with one bulk copy.  float32 rows whose entries are whole 16-byte vectors (Circle, TakeOff), long
+//        histories: D = 160 ran 75 % bank-conflict wavefronts in mode 1 (profiles/r2_h8.summary.csv)
+__host__ __device__ inline int rollout_row_stride(int D, int wmode, size_t elem) { return wmode == 2 ? D + (int)(16 / elem) : D; }
 template <class T>
-__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_tiles, int E) {
-  size_t words = (size_t)n_tiles * block * D + (size_t)4 * block;
-  if ((D & 15) == 0) words += (size_t)(block / 32) * E * 32;
+__host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_tiles, int E, int wmode) {
+  size_t words = (size_t)n_tiles * block * rollout_row_stride(D, wmode, sizeof(T)) + (size_t)4 * block;
+  if (wmode == 1) words += (size_t)(block / 32) * E * 32;
   size_t bytes = (words * sizeof(T) + 15) & ~(size_t)15;
   return bytes + sizeof(double) * 4 * block;
 }
@@ -603,7 +611,8 @@ struct StepCtx {
   bool valid;                 // i < n
   int lane, tid, B;           // lane in the warp, thread in the block, threads per block (statistics columns)
   T* row0; T* row1;           // this thread's row in the two observation tiles (row1 == row0 with one tile)
-  T* stg;                     // column-major staging buffer of the warp (WIDE only)
+  T* stg;                     // column-major staging buffer of the warp (WIDE == 1 only)
+  int RS;                     // words between the rows of two neighbouring lanes in a tile
   double* acc_sum; T* acc_ext;
   int NT;                     // observation tiles (1 or 2)
   bool fast2, bulk, latency, any_fin;
@@ -616,16 +625,17 @@ struct StepCtx {
 //  time-major buffers in a.b.  `vote(pred)`: OR of `pred` over the thread group that regenerates reset
 //  packages together (a barrier: all threads of the group call it once per step).
 // ---------------------------------------------------------------------------------------------
-// WIDE: obs_dim is a multiple of 16 (rows walked in rotated order, see below) -- a template parameter
-// because as a run-time branch it made ptxas spill the 17 words of the new entry on BOTH paths.
-template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE, class Vote>
+// WIDE: row mode (see rollout_smem_bytes) -- a template parameter because as a run-time branch it made ptxas spill
+// the 17 words of the new entry on BOTH paths.
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, int WIDE, class Vote>
 __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, PHYS, NOISE, RNG, PID>& m, StepCtx<T>& sc,
                                              const int t, const float4 a4, Vote vote) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
   constexpr int C = Mo::C, E = Mo::E;
   constexpr bool POOL = RNG == PDX_RNG_PHILOX;       // pre-computed reset packages (see gen_package)
-  constexpr bool wide = WIDE;
+  constexpr bool quad = WIDE == 2 && sizeof(T) == 4 && E % 4 == 0 && C % 4 == 0;
+  constexpr bool wide = WIDE == 1 || (WIDE == 2 && !quad);
   const DevCfg<T>& c = a.c;
   const int64_t n = sc.n, i = sc.i;
   const bool valid = sc.valid, fast2 = sc.fast2, bulk = sc.bulk, latency = sc.latency;
@@ -653,7 +663,7 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
     // the copies of the warp, so it is the lane that can wait for them).  No block-wide barrier: warps
     // run through their steps independently.
     if (!fast2) {
-      if (lane == 0) { if (NT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+      if (lane == 0 || quad) { if (NT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // (quad: a lane sends its own row)
       __syncwarp();
     }
 
@@ -666,7 +676,20 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
     // (agents.py:386, base.py:426-427), which the latency ring overwrites in place with the current action
     // -> those entries read as the *current* action for as long as they stay in the deque.
     if (valid) {
-      if constexpr (wide) {
+      if constexpr (quad) {
+        constexpr int VPE = E / 4;                         // 16-byte vectors per entry; the action is the last one
+        const float4* src = reinterpret_cast<const float4*>(to) + VPE;
+        float4* dst = reinterpret_cast<float4*>(tn);
+        for (int j = 0; j < H - 1; ++j) {
+          const bool alias = latency && (j + n_ep <= H);
+#pragma unroll
+          for (int q = 0; q < VPE; ++q) {
+            float4 v = src[j * VPE + q];
+            if (q == VPE - 1 && alias) v = make_float4((float)actT[0], (float)actT[1], (float)actT[2], (float)actT[3]);
+            dst[j * VPE + q] = v;
+          }
+        }
+      } else if constexpr (wide) {
         for (int j = 0; j < H - 1; ++j) {
           const bool alias = latency && (j + n_ep <= H);
 #pragma unroll
@@ -770,7 +793,15 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
     }
 
     // ---- newest entry of the row: [o(k), a(k-1)]
-    if constexpr (wide) {                                  // registers cannot be indexed by the rotated position:
+    if constexpr (quad) {
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(tn + (H - 1) * E);
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q)
+          dst[q] = make_float4((float)core[4 * q], (float)core[4 * q + 1], (float)core[4 * q + 2], (float)core[4 * q + 3]);
+        dst[C / 4] = make_float4((float)a_new[0], (float)a_new[1], (float)a_new[2], (float)a_new[3]);
+      }
+    } else if constexpr (wide) {                           // registers cannot be indexed by the rotated position:
 #pragma unroll                                             // column-major staging buffer of the warp
       for (int k = 0; k < C; ++k) stg[k * 32 + lane] = core[k];
 #pragma unroll
@@ -944,14 +975,23 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
     const int rows_w = (int)max((int64_t)0, min((int64_t)32, n - warp_base));     // rows of this warp's tile slice
     if (rows_w > 0) {
       T* gdst = reinterpret_cast<T*>(a.b.obs) + (tn_off + warp_base) * D;
-      const T* wt = tn - lane * D;                       // this warp's slice of this step's tile
+      const T* wt = tn - lane * sc.RS;                   // this warp's slice of this step's tile
       if (bulk) {
         fence_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_store(gdst, wt, (uint32_t)rows_w * (uint32_t)D * (uint32_t)sizeof(T));
+        if constexpr (quad) {                            // padded rows: one copy per row, issued by its lane
+          if (valid) bulk_store(gdst + lane * D, tn, (uint32_t)D * (uint32_t)sizeof(T));
+        } else {
+          __syncwarp();
+          if (lane == 0) bulk_store(gdst, wt, (uint32_t)rows_w * (uint32_t)D * (uint32_t)sizeof(T));
+        }
       } else {
         __syncwarp();
-        for (int e = lane; e < rows_w * D; e += 32) gdst[e] = wt[e];
+        if constexpr (quad) {
+          for (int r = 0; r < rows_w; ++r)
+            for (int k = lane; k < D; k += 32) gdst[r * D + k] = wt[r * sc.RS + k];
+        } else {
+          for (int e = lane; e < rows_w * D; e += 32) gdst[e] = wt[e];
+        }
         __syncwarp();
       }
     }
@@ -960,7 +1000,7 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
 // ---------------------------------------------------------------------------------------------
 //  fused multi-step env.step (+ auto-reset)
 // ---------------------------------------------------------------------------------------------
-template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, bool WIDE>
+template <class T, int TASK, int PHYS, bool NOISE, int RNG, bool PID, int WIDE>
 __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
   typedef Model<T, TASK, PHYS, NOISE, RNG, PID> Mo;
   constexpr Layout L = Mo::L;
@@ -976,10 +1016,12 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile0 = reinterpret_cast<T*>(smem_raw);
   const int NT = a.n_tiles;
-  T* tile1 = NT == 2 ? tile0 + (size_t)B * D : tile0;
-  constexpr bool wide = WIDE;
-  T* stg = tile0 + (size_t)NT * B * D + (size_t)warp * (E * 32);          // valid only when `wide`
-  const size_t words_before_acc = (size_t)NT * B * D + (wide ? (size_t)(B >> 5) * E * 32 : 0);
+  constexpr bool quad = WIDE == 2 && sizeof(T) == 4 && E % 4 == 0 && Mo::C % 4 == 0;
+  constexpr bool wide = WIDE == 1 || (WIDE == 2 && !quad);
+  const int RS = rollout_row_stride(D, quad ? 2 : 0, sizeof(T));
+  T* tile1 = NT == 2 ? tile0 + (size_t)B * RS : tile0;
+  T* stg = tile0 + (size_t)NT * B * RS + (size_t)warp * (E * 32);         // valid only when `wide`
+  const size_t words_before_acc = (size_t)NT * B * RS + (wide ? (size_t)(B >> 5) * E * 32 : 0);
   T* acc_ext = tile0 + words_before_acc;
   const size_t off = ((words_before_acc + (size_t)4 * B) * sizeof(T) + 15) & ~(size_t)15;
   double* acc_sum = reinterpret_cast<double*>(smem_raw + off);
@@ -993,8 +1035,8 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
 #pragma unroll
   for (int k = 0; k < Mo::NW; ++k) m.w[k] = T(0);        // lanes past n_envs: no pending packages, never finish
   T* state = reinterpret_cast<T*>(a.b.state);
-  T* my_row0 = tile0 + (size_t)tid * D;
-  T* my_row1 = tile1 + (size_t)tid * D;
+  T* my_row0 = tile0 + (size_t)tid * RS;
+  T* my_row1 = tile1 + (size_t)tid * RS;
   // Programmatic dependent launch: this grid may have started while the kernel before it on the stream is
   // still draining.  Nothing that kernel could have written is touched before griddepcontrol.wait (which
   // returns once it has completed and its writes are visible).  With PDX_BUF_STATE_STABLE the caller
@@ -1030,7 +1072,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
   }
   StepCtx<T> sc;
   sc.state = state; sc.n = n; sc.i = i; sc.valid = valid; sc.lane = lane; sc.tid = tid; sc.B = B;
-  sc.row0 = my_row0; sc.row1 = my_row1; sc.stg = stg; sc.acc_sum = acc_sum; sc.acc_ext = acc_ext; sc.NT = NT;
+  sc.row0 = my_row0; sc.row1 = my_row1; sc.stg = stg; sc.RS = RS; sc.acc_sum = acc_sum; sc.acc_ext = acc_ext; sc.NT = NT;
   sc.fast2 = fast2; sc.latency = Mo::BULLET && c.use_latency; sc.any_fin = false;
   // observation rows leave as one bulk copy per warp and step when the destination meets the 16-byte
   // rules of the bulk engine for every step (else: flat coalesced copy by the warp)
@@ -1054,7 +1096,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
   }
 
   // ---- epilogue: state and history back to HBM, statistics, drain the bulk engine
-  if (lane == 0) bulk_wait_read<0>();
+  if (lane == 0 || quad) bulk_wait_read<0>();
   __syncwarp();
   if (valid) {
     m.store(state, n, i, true);
@@ -1062,7 +1104,7 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
     store_history<T, E, QH>(state, n, i, L.n_quads, H, [&](int s, int idx) { return last[(s + 1) * E + idx]; });
   }
   block_reduce_episode_stats(a.b.episode_stats, acc_sum, acc_ext, B, sc.any_fin);
-  if (lane == 0) bulk_wait_all();
+  if (lane == 0 || quad) bulk_wait_all();
 }
 
 }  // namespace pdx

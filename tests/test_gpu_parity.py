@@ -414,6 +414,73 @@ def test_single_env_dropin_api():
         env.close()
 
 
+@pytest.mark.parametrize('env_id,kw,N', [('DroneCircleSimpleEnv-v0', {'observation_history_size': 8}, 4100),
+                                         ('DroneCircleBulletEnv-v0', {'observation_history_size': 4}, 1000),
+                                         ('DroneTakeOffSimpleEnv-v0', {'observation_history_size': 4, 'max_episode_steps': 7}, 333),
+                                         ('DroneTakeOffBulletEnv-v0', {'observation_history_size': 6, 'max_episode_steps': 9}, 65)])
+def test_padded_row_mode_matches_rotated_walk(env_id, kw, N):
+    """Long histories of 16-byte entries (float32 Circle / TakeOff, H >= 4, D % 16 == 0) use padded shared-memory
+    rows, 128-bit history shifts and one bulk copy per row (row mode 2); the rotated word-by-word walk (mode 1) is the
+    older path the goldens pin in float64.  Same step body, other staging: flags equal, values within
+    4e-6 x (1 + |value|) (two instantiations of the step: ptxas contracts a few products differently -- observed: 1 ulp
+    in the observed quaternion of the Bullet ids, bit-equal for the Simple ids) -- in fused launches and single steps,
+    over auto-resets and ragged warps, and for a destination that is only 4-byte aligned (no bulk copies)."""
+    import os
+    import phoenix_drone_simulation_b200 as pds
+    T = 24
+    g = torch.Generator(device='cuda').manual_seed(3)
+    acts = torch.rand((T, N, 4), device='cuda', generator=g) * 2 - 1
+    res = {}
+    try:
+        for mode in ('1', '2'):
+            os.environ['PDX_WMODE'] = mode
+            env = pds.VecEnv(env_id, N, seed=11, keep_final_obs=True, **kw)
+            assert env.obs_dim % 16 == 0
+            o0 = env.reset().clone()
+            D = env.obs_dim
+            flat = torch.zeros(16 * N * D + 1, device='cuda')
+            out = {'obs': torch.empty((16, N, D), device='cuda'), 'reward': torch.empty((16, N), device='cuda'),
+                   'cost': torch.empty((16, N), device='cuda'), 'terminated': torch.empty((16, N), dtype=torch.uint8, device='cuda'),
+                   'truncated': torch.empty((16, N), dtype=torch.uint8, device='cuda'),
+                   'final_obs': torch.zeros((16, N, D), device='cuda')}     # (only rows of finished episodes are written)
+            env.step_many(acts[:16], out)                                   # one fused launch
+            singles = [tuple(x.clone() if torch.is_tensor(x) else x['cost'].clone() for x in env.step(acts[t])) for t in range(16, 20)]
+            out_u = dict(out)
+            out_u['obs'] = flat[1:1 + 4 * N * D].view(4, N, D)             # 4-byte aligned: the warps copy the rows themselves
+            out_u = {k: (v if k == 'obs' else v[:4]) for k, v in out_u.items()}
+            out_u['final_obs'].zero_()
+            env.step_many(acts[20:24], out_u)
+            res[mode] = (o0, {k: v.clone() for k, v in out.items()}, singles, out_u['obs'].clone(),
+                         {nm: env.get_state(nm) for nm in ('xyz', 'vel', 'ou', 'last_action', 'ep_return', 'ep_length', 'hist', 'dt', 'mass', 'ep_index')},
+                         env.episode_stats().clone())
+    finally:
+        os.environ.pop('PDX_WMODE', None)
+    a, b = res['1'], res['2']
+
+    def same(x, y, what):
+        if x.dtype in (torch.uint8, torch.bool):
+            assert torch.equal(x, y), what
+        else:
+            err = float(((x.double() - y.double()).abs() / (1 + y.double().abs())).max())
+            assert err <= 4e-6, (what, err)
+            if 'Simple' in env_id:
+                assert torch.equal(x, y), what
+    same(a[0], b[0], 'reset')
+    for k in a[1]:
+        same(a[1][k], b[1][k], k)
+    for sa, sb in zip(a[2], b[2]):
+        for xa, xb in zip(sa, sb):
+            same(xa, xb, 'single step')
+    same(a[3], b[3], 'unaligned destination')
+    # (the two modes may pick different block sizes: package regeneration is voted per block, so the pool part of the
+    # state and the order of the statistics' atomics may differ; everything an episode can observe may not)
+    for name in ('xyz', 'vel', 'ou', 'last_action', 'ep_return', 'ep_length', 'hist', 'dt', 'mass'):
+        same(a[4][name], b[4][name], name)
+    assert torch.equal(a[4]['ep_index'] // 16, b[4]['ep_index'] // 16)
+    torch.testing.assert_close(a[5], b[5], rtol=1e-5, atol=0)
+    assert int(a[5][0]) > 0, 'no episode ended: the reset path of the padded rows was not exercised'
+
+
 @pytest.mark.parametrize('env_id,kw', [('DroneHoverSimpleEnv-v0', {}), ('DroneCircleBulletEnv-v0', {}),
                                        ('DroneCircleSimpleEnv-v0', {'observation_history_size': 8}),
                                        ('DroneTakeOffSimpleEnv-v0', {'max_episode_steps': 7})])
