@@ -288,6 +288,37 @@ def time_e2e(env, inner, K, W, dist_ctx, gen_seed):
     return ms, pipe['h2d_bytes'], pipe['d2h_bytes']
 
 
+def link_ceiling(dev, dist_ctx, mbytes=512, reps=4):
+    """What this box's host link gives a rank while ALL ranks copy at the same time: pinned D2H alone, and D2H with a
+    concurrent H2D of 1/9 of the size (the e2e leg's ratio), GB/s per rank -- the ceiling the e2e number is a
+    fraction of (its timed region moves d2h_bytes_per_step over this link)."""
+    import torch
+    n = mbytes << 20
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d2 = torch.empty(n // 9, dtype=torch.uint8, device=dev)
+    h2 = torch.empty(n // 9, dtype=torch.uint8).pin_memory()
+    s_out, s_in = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    out = {}
+    for both in (False, True):
+        for timed in (False, True):
+            dist_ctx.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_out)
+            for _ in range(reps if timed else 1):
+                with torch.cuda.stream(s_out):
+                    h.copy_(d, non_blocking=True)
+                if both:
+                    with torch.cuda.stream(s_in):
+                        d2.copy_(h2, non_blocking=True)
+            e1.record(s_out)
+            torch.cuda.synchronize()
+            ms = dist_ctx.max_over_ranks(e0.elapsed_time(e1))
+        out['d2h_with_h2d_gbs' if both else 'd2h_gbs'] = reps * n / (ms * 1e-3) / 1e9
+    return out
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Host side of the e2e leg: keep this rank's threads (and therefore its pinned staging buffers,
     first-touch) on the NUMA node its GPU hangs off; otherwise eight ranks share one node's memory
@@ -527,8 +558,12 @@ def run_gpu_arm(a):
     e2e_ms, h2d, d2h = time_e2e(env, a.inner, e2e_k * a.launches, min(a.warmup, 3), ctx, 99 + ctx.rank)
     h2d, d2h = h2d * a.launches, d2h * a.launches
     e2e_steps = e2e_k * a.launches * a.inner * n * ctx.world
+    link = link_ceiling(ctx.device, ctx)
+    e2e_d2h_gbs = d2h * e2e_k / (e2e_ms * 1e-3) / 1e9            # per rank
     e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'numa_node_rank0': ctx.numa_node,
+           'link': dict(link, achieved_d2h_gbs_per_rank=e2e_d2h_gbs, frac_of_d2h_ceiling=e2e_d2h_gbs / link['d2h_with_h2d_gbs'],
+                        what='pinned-memory copy ceiling of this box with all ranks copying at once, per rank (measured here)'),
            'api': 'VecEnv.step_many_host: pinned host action/obs/reward/cost/flag buffers, H2D + launch + D2H per 8-step chunk on three streams, all inside the timed region'}
 
     extra = {}

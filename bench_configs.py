@@ -4,7 +4,7 @@ bench.py (which measures configs[1], the headline).  Prints one JSON line per co
 the lines committed under profiles/ come from this script run under gpurun.
 
     python bench_configs.py [--scale 1.0] [--steps 20] [--warmup 3]
-    torchrun --nproc-per-node N ... bench_configs.py --only "configs[4]"     # configs[4] on N GPUs
+    torchrun --nproc-per-node N ... bench_configs.py --only "configs[4]"     # configs[4] on N GPUs (also: "configs[2]", "configs[3]")
 
 configs[2]  DroneCircleSimpleEnv-v0, 524,288 envs per GPU (4 Mi over 8 GPUs), H = 2 and H = 8
 configs[3]  DroneTakeOffSimpleEnv-v0, 1 Mi envs, ground effect on, obs noise, auto-reset (time limit
@@ -24,7 +24,12 @@ from phoenix_drone_simulation_b200.rollout import ActorCritic, RolloutCollector
 
 
 def open_loop(env_id, n, inner, steps, warmup, action_fn, **kw):
-    env = VecEnv(env_id, n, seed=1, **kw)
+    """n environments PER GPU.  Under torchrun every rank steps its own shard (env_offset: the draws are those of one
+    job of world x n environments); environments are independent, so the data path has no collective -- the episode
+    statistics are summed once after the timed region; time = max over ranks."""
+    dist, rank, world = _dist()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    env = VecEnv(env_id, n, device=dev, seed=1, env_offset=rank * n, **kw)
     env.reset()
     dev, d = env.device, env.obs_dim
     g = torch.Generator(device=dev).manual_seed(0)
@@ -35,6 +40,8 @@ def open_loop(env_id, n, inner, steps, warmup, action_fn, **kw):
             'truncated': torch.empty((inner, n), dtype=torch.uint8, device=dev)} for _ in range(2)]
     for k in range(warmup):
         env.step_many(acts[k & 1], out[k & 1])
+    if dist:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -44,10 +51,20 @@ def open_loop(env_id, n, inner, steps, warmup, action_fn, **kw):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     nonfinite = int((~torch.isfinite(out[0]['obs'])).sum()) + int((~torch.isfinite(out[0]['reward'])).sum())
-    s = env.episode_stats().cpu().tolist()
+    st = env.episode_stats()
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.cat([st[:4], torch.tensor([nonfinite], dtype=st.dtype, device=dev)])
+        dist.all_reduce(tot)
+        st = torch.cat([tot[:4], st[4:]])
+        nonfinite = int(tot[4])
+    s = st.cpu().tolist()
     bytes_per = env.rollout_bytes(inner) / inner
+    n = n * world
     v = steps * inner * n / (ms * 1e-3)
-    return {'env_id': env_id, 'envs': n, 'obs_dim': d, 'kwargs': {k: (v2 if not isinstance(v2, bool) else int(v2)) for k, v2 in kw.items()},
+    return {'env_id': env_id, 'envs': n, 'n_gpus': world, 'obs_dim': d, 'kwargs': {k: (v2 if not isinstance(v2, bool) else int(v2)) for k, v2 in kw.items()},
             'env_steps_per_s': v, 'ms_per_launch': ms / steps, 'env_steps_per_launch': inner * n,
             'algorithmic_bytes_per_env_step': bytes_per, 'algorithmic_GBps': v * bytes_per / 1e9,
             'nonfinite_words_in_last_segment': nonfinite, 'episodes_finished': int(s[0]), 'mean_episode_length': (s[3] / s[0]) if s[0] else None}
@@ -148,7 +165,9 @@ def main():
     import os
     emit = lambda ln: print(json.dumps(ln), flush=True) if int(os.environ.get('RANK', '0')) == 0 else None
     if a.only:
-        lines = {'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 3, k)))
+        lines = {'configs[2] H=2': lambda: emit(dict(config='configs[2] H=2', **open_loop(
+                     'DroneCircleSimpleEnv-v0', sc(524288), 16, a.steps, a.warmup, uniform_actions))),
+                 'configs[4]': lambda: [emit(dict(config=f'configs[4] policy_kernel={k}', **ppo_rollout(sc(131072), 64, max(2, a.steps // 5), 3, k)))
                                         for k in a.kernels.split(',')],
                  'configs[2] H=8': lambda: emit(dict(config='configs[2] H=8', **open_loop(
                      'DroneCircleSimpleEnv-v0', sc(524288), 8, a.steps, a.warmup, uniform_actions, observation_history_size=8))),

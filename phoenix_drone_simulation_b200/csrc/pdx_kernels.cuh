@@ -19,6 +19,9 @@
 #ifndef PDX_FAST2
 #define PDX_FAST2 1
 #endif
+#ifndef PDX_ACT_PREFETCH
+#define PDX_ACT_PREFETCH 1          // next step's action line: 1 = into L2, 2 = into L1 (+ the one after into L2), 3 = into L1
+#endif
 #ifndef PDX_PREFETCH
 #define PDX_PREFETCH 1
 #endif
@@ -1086,7 +1089,14 @@ __global__ void __maxnreg__(128) k_rollout(const __grid_constant__ KArgs<T> a) {
     if (valid) {
       const float4* ap = reinterpret_cast<const float4*>(a.actions) + (int64_t)t * n + i;
       a4 = *ap;
+#if PDX_ACT_PREFETCH == 1
       if (t + 1 < a.n_steps) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + n));
+#elif PDX_ACT_PREFETCH == 2
+      if (t + 1 < a.n_steps) asm volatile("prefetch.global.L1 [%0];" ::"l"(ap + n));
+      if (t + 2 < a.n_steps) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 2 * n));
+#elif PDX_ACT_PREFETCH == 3
+      if (t + 1 < a.n_steps) asm volatile("prefetch.global.L1 [%0];" ::"l"(ap + n));
+#endif
     }
     // Package regeneration is voted per BLOCK: all warps of a block run the (long) generator at the same
     // step, and the barrier keeps them within one step of each other -- the step is ~30 KB of straight-line
