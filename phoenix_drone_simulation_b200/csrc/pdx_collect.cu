@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
     }
     StepCtx<T> sc;
     sc.state = state; sc.n = n; sc.i = i; sc.valid = valid; sc.lane = lane; sc.tid = tid; sc.B = B;
-    sc.row0 = my_row; sc.row1 = my_row; sc.stg = nullptr; sc.RS = D; sc.acc_sum = acc_sum; sc.acc_ext = acc_ext; sc.NT = 1;
+    sc.row0 = my_row; sc.row1 = my_row; sc.stg = nullptr; sc.RS = D; sc.next_ap = nullptr; sc.acc_sum = acc_sum; sc.acc_ext = acc_ext; sc.NT = 1;
     sc.fast2 = false; sc.latency = Mo::BULLET && c.use_latency; sc.any_fin = false;
     sc.bulk = ((reinterpret_cast<uintptr_t>(a.b.obs) | (uintptr_t)((uint64_t)n * D * sizeof(T))) & 15u) == 0 &&
               (((uint64_t)max((int64_t)0, min((int64_t)32, n - (i - lane))) * D * sizeof(T)) & 15u) == 0;
