@@ -550,6 +550,13 @@ def run_gpu_arm(a):
                     'peak_source': f'{props.multi_processor_count} SMs x 4 schedulers x {sm_mhz} MHz (median SM clock under load)'}
     else:
         roofline = dict(hbm, bound='hbm', traffic=None)
+    # SURVEY 8(d) sized the path as HBM-bound with the state read and written on EVERY env.step (542 B per env-step
+    # for Hover-Simple H=2, ceiling = peak / 542 B): the fused launch keeps the state in registers across its steps,
+    # which is why the line above is bounded by issue slots instead.  Reported for reference, not as the roofline.
+    per_step_stream = {'bytes_per_env_step': 542, 'ceiling_env_steps_per_s': hbm['peak'] * 1e9 / 542,
+                       'achieved_over_ceiling': (steps_per_launch * n / (us_per_launch * 1e-6)) / (hbm['peak'] * 1e9 / 542),
+                       'what': 'SURVEY 8(d): state streamed through HBM on every env.step (a per-step kernel could not exceed this)'}
+    roofline.update({'per_step_streaming': per_step_stream})
     roofline.update({'hbm': hbm, 'kernel': 'pdx::k_rollout<float, hover, simple, noise, philox>',
                      'env_steps_per_launch': steps_per_launch * n, 'us_per_launch': us_per_launch})
 
