@@ -6,6 +6,13 @@
   2. the oracle on the draws the production Philox path really consumed (pdx_dump_draws);
   3. size-independent properties at BASELINE.json's full size (65,536 envs).
 
+What the goldens pin: for the *SimpleEnv ids every line of arithmetic is the reference's own (only three pure
+quaternion helpers come from the pybullet stand-in).  For the *BulletEnv ids the motor lag, latency ring, noise,
+observation, reward and reset logic are the reference's, but the rigid-body integrator behind `stepSimulation()` is
+the stand-in's single-rigid-body restatement (oracle/shim/pybullet.py; no PyBullet binary exists in this image): with
+respect to that integrator the Bullet goldens are SELF-CONSISTENCY tests (oracle == stand-in == kernel), not parity
+with real Bullet -- DESIGN.md section 1 calls this "parity unpinned".
+
 Everything here needs a CUDA device (`-m gpu`) and nothing reads /root/reference.
 """
 import numpy as np
