@@ -37,8 +37,13 @@
 // Tuning hooks (tools/build_variant.sh, tools/ab_collect.sh).  Both "lighter" synchronisations measured SLOWER on
 // configs[4] (1408 us with the barriers, 1419 us with leader-only waits, 1455 us with the counter release): the
 // barriers keep the four warps of a tile on the same instructions, and the loop body (159 KB of SASS) lives or dies
-// by instruction-cache sharing.
+// by instruction-cache sharing.  Also slower: keeping two 16-column tcgen05.ld chunks in flight in the epilogues
+// (software prefetch of the next chunk, 1,508 vs 1,420 us) -- more live registers and code for a latency the other
+// tiles already cover.
 #define PDX_COL_LEADER_WAIT 0        // 1 = only the issuing warp waits at the hand-off barriers, the others arrive
+#endif
+#ifndef PDX_COL_NANOSLEEP
+#define PDX_COL_NANOSLEEP 40         // back-off of the slot spin in ns (200: +1 % kernel time)
 #endif
 #ifndef PDX_COL_COUNTER_RELEASE
 #define PDX_COL_COUNTER_RELEASE 0    // 1 = the tile's last warp out of the layer-2 epilogue releases the slot (no barrier)
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
 #pragma unroll
           for (int q = 0; q < Cfg::kSlots; ++q)
             if (s < 0 && atomicCAS(&slot_busy[q], 0u, 1u) == 0u) s = q;
-          if (s < 0) { __nanosleep(200); if (it > (1u << 24)) __trap(); }
+          if (s < 0) { __nanosleep(PDX_COL_NANOSLEEP); if (it > (1u << 24)) __trap(); }
         }
         __threadfence_block();
         tile_info[tile] = (uint32_t)s | (slot_phase[s] << 8);
