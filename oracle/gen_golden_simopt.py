@@ -107,6 +107,22 @@ def main():
     np.savez_compressed(out, observations=O, actions=A, pre_inputs=P, candidates=cands, losses=losses)
     print('mini-trajectories', O.shape, 'losses per candidate', losses.mean(1))
 
+    # Latency as a parameter (set_parameters -> set_latency, agents.py:388-404): none (below one 5 ms sub-step), 1, 2,
+    # 3 (0.015 / 0.005 = 3.0000000000000004), 4, 7 and 10 sub-steps of delay
+    cands = np.array([[1.8, 0.08, 0.0], [1.8, 0.08, 0.004], [1.93, 0.11, 0.005], [1.93, 0.11, 0.0125], [2.2, 0.05, 0.015],
+                      [2.0, 0.1, 0.021], [1.7, 0.06, 0.0351], [2.1, 0.09, 0.05]])
+    losses = np.zeros((len(cands), len(O)))
+    rings = []
+    for k, c in enumerate(cands):
+        of.set_parameters(c)
+        d = of.sim_env.drone
+        rings.append(d.buf_size if d.use_latency else 0)
+        for m in range(len(O)):
+            losses[k, m] = of.evaluate_once(O[m], A[m], pre_inputs=P[m])
+    out = os.path.join(ROOT, 'tests', 'golden_collector', 'simopt_hover_latency.npz')
+    np.savez_compressed(out, observations=O, actions=A, pre_inputs=P, candidates=cands, losses=losses, ring_lengths=np.array(rings))
+    print('latency candidates: ring lengths', rings, 'losses per candidate', losses.mean(1))
+
 
 if __name__ == '__main__':
     main()

@@ -323,6 +323,19 @@ class OracleEnv:
     # ----------------------------------------------------------------------------------------
     #  control.act: control.py:94-100 (PWM), :120-191 (AttitudeRate), :194-287 (Attitude)
     # ----------------------------------------------------------------------------------------
+    def set_latency(self, new_latency):
+        """agents.py:388-404 (called by the simulation-optimisation objective): NOTE the true division, where the
+        constructor (agents.py:180) floors -- 0.015 s is 3 sub-steps here and 2 there."""
+        self.latency = new_latency
+        if new_latency < self.TIME_STEP:
+            self.use_latency = False
+        else:
+            self.use_latency = True
+            self.buf_size = int(new_latency / self.TIME_STEP)
+            assert self.buf_size > 0
+            self.ring = np.zeros((self.buf_size, 4))
+            self.ring_idx = 0
+
     def _rate_pid(self, rpy_dot_target):
         dt = self.TIME_STEP
         error = (rpy_dot_target - self.omega) * 180. / np.pi

@@ -39,7 +39,7 @@ def set_parameters(env, params):
     env.A = np.ones(4) * (1 - env.dt / T)
     env.B = np.ones(4) * (env.dt / T)
     env.K = np.ones(4) * (0.028 * env.G * p[0] / 4)       # agents.py:224
-    assert int(p[2] / env.TIME_STEP) == env.ring.shape[0], 'the oracle keeps the constructor ring length'
+    env.set_latency(p[2])                                 # pybullet.py:248 -> agents.py:388-404
 
 
 def loss_function(obs_sim, obs_real):

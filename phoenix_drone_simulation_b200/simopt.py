@@ -13,8 +13,14 @@ to real-flight logs by replaying mini-trajectories one at a time and one candida
 Here every (candidate, mini-trajectory) pair is one environment of a VecEnv: K candidates x M
 mini-trajectories are evaluated with one reset, `pre_steps` single-step launches and ONE fused
 launch.  Per-environment parameters are the motor words of the state (`motor_b` = Ts / T,
-`motor_k` = 0.028 g t2w / 4, agents.py:222-224); the latency (ring length) is structural in the
-engine and therefore common to all candidates of one objective.
+`motor_k` = 0.028 g t2w / 4, agents.py:222-224).
+
+Latency as a parameter (third candidate column; simopt/pybullet.py:248 -> agents.py:388-404 `set_latency`): the
+reference's ring holds L = int(latency / TIME_STEP) sub-steps (none below one sub-step).  The objective replays
+KNOWN action sequences, so a ring of L sub-steps is a ring of r in {1, 2} sub-steps (what the engine's registers hold)
+behind a sequence delayed by m whole steps, L = 2 m + r (two sub-steps per step): the controller of sub-step s sees
+the action of step (s - L) // 2 either way, and zeros -- the cleared ring -- before that.  Candidates are grouped by r
+(0 = no latency); each group runs on its own VecEnv with its own, per-environment delayed action tensor.
 """
 import math
 
@@ -58,9 +64,10 @@ def rot_from_quat(q):
 
 class TrajectoryObjective:
     """observations [M, T, 12] = (xyz, xyz_dot, rpy, body rates) logs, actions [M, T, 4] in [-1, 1],
-    pre_inputs [M, P, 4]; `evaluate(candidates [K, 2] = (thrust-to-weight, motor time constant))`
-    returns the K objective values of simopt/pybullet.py:72-128; `evaluate(..., per_trajectory=True)` the
-    [K, M] losses of evaluate_once (pybullet.py:130-183) themselves."""
+    pre_inputs [M, P, 4]; `evaluate(candidates [K, 2] = (thrust-to-weight, motor time constant))` or
+    `[K, 3] = (..., latency in seconds)` returns the K objective values of simopt/pybullet.py:72-128;
+    `evaluate(..., per_trajectory=True)` the [K, M] losses of evaluate_once (pybullet.py:130-183) themselves.
+    Without a latency column the latency of the environment's configuration applies to every candidate."""
 
     def __init__(self, observations, actions, pre_inputs, env_id='DroneHoverBulletEnv-v0', device='cuda',
                  dtype=torch.float64, gamma=0.95, seed=0, **env_kwargs):
@@ -73,20 +80,60 @@ class TrajectoryObjective:
         kw = dict(domain_randomization=-1, observation_noise=-1, auto_reset=False, enable_reset_distribution=False)
         kw.update(env_kwargs)
         self.env_id, self.device, self.dtype, self.gamma, self.seed, self.kw = env_id, device, dtype, gamma, seed, kw
-        self._env = None
+        self._envs = {}
 
-    def _make(self, n):
-        if self._env is None or self._env.num_envs != n:
-            self._env = VecEnv(self.env_id, n, device=self.device, dtype=self.dtype, seed=self.seed, **self.kw)
-            assert self._env.cfg.physics == 'PyBulletPhysics', 'the objective fits the motor model of the Bullet ids'
-        return self._env
+    def _make(self, n, ring=None):
+        """VecEnv of n environments; ring = None: the configured latency, 0 / 1 / 2: latency ring of that many sub-steps."""
+        env = self._envs.get(ring)
+        if env is None or env.num_envs != n:
+            kw = dict(self.kw)
+            if ring is not None:
+                kw['latency'] = {0: 0.0, 1: 0.005, 2: 0.0125}[ring]      # agents.py:165,180 with TIME_STEP = 1 / 200
+            env = self._envs[ring] = VecEnv(self.env_id, n, device=self.device, dtype=self.dtype, seed=self.seed, **kw)
+            assert env.cfg.physics == 'PyBulletPhysics', 'the objective fits the motor model of the Bullet ids'
+            if ring is not None:
+                assert env.pdx.agg == 2 and abs(env.pdx.time_step - 0.005) < 1e-12, 'latency candidates: 200 Hz sub-steps, two per step'
+                assert (env.pdx.use_latency, env.pdx.buf_size if ring else 1) == (int(ring > 0), max(ring, 1))
+        return env
+
+    @staticmethod
+    def ring_length(latency, time_step=0.005):
+        """Sub-steps of delay of `set_latency` (agents.py:388-404): none below one sub-step, else int(latency / TIME_STEP)
+        -- true division, unlike the constructor's floor division (0.015 s: 3 here, 2 there)."""
+        return 0 if latency < time_step else int(latency / time_step)
 
     @torch.no_grad()
     def evaluate(self, candidates, per_trajectory=False):
-        cand = torch.as_tensor(candidates, dtype=torch.float64, device=self.device).reshape(-1, 2)
+        cand = torch.as_tensor(candidates, dtype=torch.float64, device=self.device)
+        cand = cand.reshape(-1, cand.shape[-1])
+        if cand.shape[1] == 2:
+            return self._evaluate_group(cand, None, None, per_trajectory)
+        assert cand.shape[1] == 3, 'candidates: (thrust-to-weight, motor time constant[, latency])'
+        L = [self.ring_length(float(x)) for x in cand[:, 2].tolist()]
+        res = torch.empty((cand.shape[0], self.M), dtype=torch.float64, device=self.device)
+        for ring in (0, 1, 2):                                   # L = 2 m + r
+            ks = [k for k, l in enumerate(L) if (l == 0 and ring == 0) or (l > 0 and 2 - l % 2 == ring)]
+            if ks:
+                shift = torch.tensor([(L[k] - ring) // 2 for k in ks], device=self.device)
+                res[ks] = self._evaluate_group(cand[ks, :2], ring, shift, True)
+        return res if per_trajectory else res.mean(1)
+
+    def _delayed(self, seq, shift):
+        """seq [M, S, 4] -> [K, M, S, 4]: candidate k sees seq delayed by shift[k] steps, zeros (the cleared ring) first."""
+        K, S = shift.shape[0], seq.shape[1]
+        t = torch.arange(S, device=self.device)[None, :] - shift[:, None]                  # [K, S]
+        out = seq[:, t.clamp_min(0)]                                                       # [M, K, S, 4]
+        return (out * (t >= 0)[None, :, :, None]).transpose(0, 1)
+
+    def _evaluate_group(self, cand, ring, shift, per_trajectory):
         K, M, T = cand.shape[0], self.M, self.T
-        env = self._make(K * M)
+        env = self._make(K * M, ring)
         rep = lambda x: x.unsqueeze(0).expand(K, *x.shape).reshape(K * M, *x.shape[1:])
+        if shift is None:
+            pre_seq, act_seq = rep(self.pre), rep(self.act[:, :T - 1])
+        else:
+            pre_seq = self._delayed(self.pre, shift).reshape(K * M, *self.pre.shape[1:])
+            act_seq = self._delayed(self.act[:, :T - 1], shift).reshape(K * M, T - 1, 4)
         # 1) reset, candidate parameters (update_motor_dynamics), pre-steps for the motor state
         env.reset()
         ts = env.pdx.time_step
@@ -94,7 +141,7 @@ class TrajectoryObjective:
         env.set_state('motor_b', (ts / tau).repeat_interleave(M)[:, None].expand(-1, 4))
         env.set_state('motor_k', (0.028 * 9.81 * t2w / 4).repeat_interleave(M)[:, None].expand(-1, 4))
         for j in range(self.pre.shape[1]):
-            env.step(rep(self.pre[:, j]).contiguous())
+            env.step(pre_seq[:, j].contiguous())
         # 2) logged initial state: pose, velocities, cleared latency ring.  quirk kept (verified against the reference,
         # tests/golden_collector/simopt_hover.npz): evaluate_once stores R w_logged as init_rpy_dot
         # (pybullet.py:153-154) and task_specific_reset hands R^T init_rpy_dot to Bullet as the WORLD rate
@@ -109,7 +156,7 @@ class TrajectoryObjective:
             env.set_state(name, torch.zeros((K * M, width), dtype=torch.float64, device=self.device))
         # 3) replay the logged actions in one fused launch
         n, d = K * M, env.obs_dim
-        acts = rep(self.act[:, :T - 1]).transpose(0, 1).contiguous()                      # [T-1, n, 4]
+        acts = act_seq.transpose(0, 1).contiguous()                                        # [T-1, n, 4]
         out = {'obs': torch.empty((T - 1, n, d), dtype=self.dtype, device=self.device),
                'reward': torch.empty((T - 1, n), dtype=self.dtype, device=self.device),
                'cost': torch.empty((T - 1, n), dtype=self.dtype, device=self.device),

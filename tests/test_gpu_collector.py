@@ -490,6 +490,23 @@ def test_simopt_objective_matches_reference_losses():
     np.testing.assert_allclose(obj.evaluate(g['candidates'][:, :2]).cpu().numpy(), g['losses'].mean(1), rtol=0, atol=1e-6)
 
 
+def test_simopt_objective_fits_latency_like_the_reference():
+    """Latency as the third fitted parameter (simopt/pybullet.py:248 -> agents.py:388-404): rings of 0, 0, 1, 2, 3, 4, 7
+    and 10 sub-steps against the losses of the UNMODIFIED reference (tests/golden_collector/simopt_hover_latency.npz).
+    The engine's ring holds one or two sub-steps; longer rings are that ring behind a per-environment delayed action
+    sequence (simopt.py).  Tolerance 1e-6 as above (float32 actions)."""
+    from phoenix_drone_simulation_b200.simopt import TrajectoryObjective
+    g = _load('simopt_hover_latency')
+    obj = TrajectoryObjective(g['observations'], g['actions'], g['pre_inputs'], motor_thrust_noise=0.0)
+    L = obj.evaluate(g['candidates'], per_trajectory=True).cpu().numpy()
+    err = np.abs(L - g['losses']).max(1)
+    print('simopt latency candidates: ring lengths', [int(x) for x in g['ring_lengths']], 'max abs err per candidate', ' '.join(f'{e:.1e}' for e in err))
+    assert err.max() <= 1e-6
+    np.testing.assert_allclose(obj.evaluate(g['candidates']).cpu().numpy(), g['losses'].mean(1), rtol=0, atol=1e-6)
+    # latency matters: the candidates that differ only in their ring length have different losses
+    assert abs(g['losses'][2].mean() - g['losses'][3].mean()) > 1e-3
+
+
 def test_engine_reproduces_reference_roll_out_golden():
     """The golden rollout recorded from the UNMODIFIED reference's IWPGAlgorithm.roll_out (iwpg.py:350-385;
     oracle/gen_golden_rollout.py) through the engine's pieces:
