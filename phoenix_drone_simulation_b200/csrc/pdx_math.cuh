@@ -235,52 +235,4 @@ struct Rng {
   }
 };
 
-// ---- reset draws generated cooperatively by a warp ------------------------------------------
-// The draws of one env.reset() occupy the sites SITE_RESET .. SITE_RESET_OBS2 + 6.  In the
-// production path the lanes of a warp generate them together for the (few) environments of the
-// warp that finished an episode, one Philox call per work item, into a shared-memory table
-//   tab[(site - SITE_RESET) * 4 + word][slot]     (kResetChunk slots per pass)
-// and the owner lane then runs the reset arithmetic reading its column (TableRng below has the
-// draw interface of Rng).  Same sites, same words, same conversions as Rng -> same numbers.
-constexpr int kResetChunk = 8;
-constexpr int kResetRows = SITE_RESET_OBS2 + 6 - SITE_RESET;      // 30 site rows of 4 words
-
-__host__ __device__ constexpr bool reset_site_is_normal(uint32_t site) {
-  return (site >= SITE_RESET + 4 && site <= SITE_RESET + 6) ||
-         (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 3) ||
-         (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 3);
-}
-// is `site` drawn by a reset of this flavour?  (superset over the run-time switches)
-__host__ __device__ constexpr bool reset_site_used(uint32_t site, int task, bool bullet, bool noise) {
-  if (site >= SITE_RESET && site <= SITE_RESET + 6) {
-    const int k = (int)(site - SITE_RESET);
-    if (task == PDX_TASK_TAKEOFF) return k == 0;
-    return k <= 5 || bullet;
-  }
-  if (site >= SITE_DR && site <= SITE_DR + 3) return site - SITE_DR <= 1 || bullet;
-  if (site >= SITE_RESET_OBS1 && site <= SITE_RESET_OBS1 + 5) return noise;
-  if (site >= SITE_RESET_OBS2 && site <= SITE_RESET_OBS2 + 5) return noise;
-  return false;
-}
-template <class T>
-struct TableRng {
-  static constexpr bool kTape = false;
-  const T* tab;     // column of this environment: value (row, word) at tab[(row * 4 + word) * kResetChunk]
-  __device__ __forceinline__ bool dumping() const { return false; }
-  __device__ __forceinline__ void dump_value(int, double) const {}
-  template <int K>
-  __device__ __forceinline__ void fetch(uint32_t site0, T* out) const {
-    const int r0 = (int)(site0 - SITE_RESET) * 4;
-#pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = tab[(r0 + k) * kResetChunk];
-  }
-  template <int K> __device__ __forceinline__ void gen_normals(uint32_t s0, T* out) const { fetch<K>(s0, out); }
-  template <int K> __device__ __forceinline__ void gen_uniforms(uint32_t s0, T* out) const { fetch<K>(s0, out); }
-  __device__ __forceinline__ bool exact_draws() const { return false; }
-  template <int K> __device__ __forceinline__ void normals_at(uint32_t s0, int, const int (&)[K], T* out) const { fetch<K>(s0, out); }
-  template <int K> __device__ __forceinline__ void uniforms_at(uint32_t s0, int, const int (&)[K], T* out) const { fetch<K>(s0, out); }
-  template <int K> __device__ __forceinline__ void normals(uint32_t s0, int, T* out) const { fetch<K>(s0, out); }
-  template <int K> __device__ __forceinline__ void uniforms(uint32_t s0, int, T* out) const { fetch<K>(s0, out); }
-};
-
 }  // namespace pdx
