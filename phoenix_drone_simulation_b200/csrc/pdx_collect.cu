@@ -39,7 +39,10 @@
 // barriers keep the four warps of a tile on the same instructions, and the loop body (159 KB of SASS) lives or dies
 // by instruction-cache sharing.  Also slower: keeping two 16-column tcgen05.ld chunks in flight in the epilogues
 // (software prefetch of the next chunk, 1,508 vs 1,420 us) -- more live registers and code for a latency the other
-// tiles already cover.
+// tiles already cover.  Also slower: separate locks for the operand buffer X and the TMEM slot with one X buffer
+// per tile (X built while other tiles hold the slots, buffer released after layer 1, per-tile mbarriers): 1,470 vs
+// 1,400 us single TF32, 2,625 vs 2,295 us split TF32 -- every tile then queues for a slot at the same moment, where
+// the single lock staggers the tiles by itself.
 #define PDX_COL_LEADER_WAIT 0        // 1 = only the issuing warp waits at the hand-off barriers, the others arrive
 #endif
 #ifndef PDX_COL_NANOSLEEP
