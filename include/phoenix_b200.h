@@ -280,7 +280,9 @@ int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float
  * Step t draws the environment noise at `counter + t` (as pdx_step_many) and the action noise at
  * policy->counter + t with the Philox stream of pdx_policy_step_tc keyed by the GLOBAL environment index.
  * Supported: float32, Philox, observation noise on, PWM control, the Hover and Circle ids (obs_dim <= 64 and not a
- * multiple of 16), auto_reset; PDX_ERR_INVALID otherwise (callers then alternate pdx_policy_step_tc and pdx_step). */
+ * multiple of 16), auto_reset, two hidden layers of <= 64 units with the actor's first layer <= 63 (the kernel
+ * appends a constant-1 unit that carries the layer-2 biases through the MMAs); PDX_ERR_INVALID otherwise (callers
+ * then alternate pdx_policy_step_tc and pdx_step). */
 typedef struct PdxPolicy {
   int32_t obs_dim;
   int32_t precision;            /* 1 = operands rounded to TF32 once, 3 = split TF32 (float32-level results) */

@@ -16,7 +16,8 @@
 //     step of a tile is tcgen05 work on a SLOT (a range of TMEM columns plus one operand buffer):
 //     every thread standardises its own observation row into the K-major operand tile X, the tile's
 //     first warp issues layer 1 (X . B1, both nets, N = 128), every thread runs the layer-1 epilogue of
-//     ITS row (bias, relu / tanh, TF32 rounding, written back to TMEM in place), layer 2 takes its A operand
+//     ITS row (relu / tanh, TF32 rounding, written back to TMEM in place; the biases came in through a
+//     constant-1 column of X, see tc_k1), layer 2 takes its A operand
 //     from TMEM, and the layer-2 epilogue ends in the 64 x 4 + 64 dot products of layer 3, the Gaussian
 //     draw and the log-probability -- the action never leaves the thread's registers on its way into
 //     env.step.  There are no dedicated epilogue or issuer warps: while one tile waits for the tensor
