@@ -285,7 +285,8 @@ int pdx_policy_step_tc(int64_t n, int32_t obs_dim, const float* obs, const float
  * then alternate pdx_policy_step_tc and pdx_step). */
 typedef struct PdxPolicy {
   int32_t obs_dim;
-  int32_t precision;            /* 1 = operands rounded to TF32 once, 3 = split TF32 (float32-level results) */
+  int32_t precision;            /* 1 = single-TF32 operands (float32 data, low 13 mantissa bits dropped by the tensor core), */
+                                /* 3 = split TF32 (float32-level results)                                                    */
   const float* mean;            /* observation normaliser (utils/online_mean_std.py:42-48); std == NULL skips it */
   const float* std;
   float eps;

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         for (int j = 0; j < 4; ++j) {
           const float2 nm = norm[4 * kc + j];
           const float x = (my_row[4 * kc + j] - nm.x) * nm.y;
-          hi[j] = tf32_rna(x);
+          hi[j] = X3 ? tf32_rna(x) : __float_as_uint(x);      // single TF32: the tensor core drops the low 13 bits itself
           lo[j] = x - __uint_as_float(hi[j]);
         }
         *reinterpret_cast<uint4*>(xh + kc * kLboA + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
           const int k = 4 * kc + j;
           float x = k == D ? 1.0f : 0.0f;                       // column D: constant 1 (row D of B1 = the layer-1 biases)
           if (k < D) { const float2 nm = norm[k]; x = (my_row[k] - nm.x) * nm.y; }
-          hi[j] = tf32_rna(x);
+          hi[j] = X3 ? tf32_rna(x) : __float_as_uint(x);
           lo[j] = x - __uint_as_float(hi[j]);
         }
         *reinterpret_cast<uint4*>(xh + kc * kLboA + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
         for (int j = 0; j < 16; ++j) {
           const float x = __uint_as_float(r[j]);                // (the bias came in through the constant-1 column of X)
           const float y = ch < 4 ? fmaxf(x, 0.0f) : (X3 ? tanh_fast(x) : tanh_mufu(x));
-          r[j] = tf32_rna(y);
-          lo[j] = __float_as_uint(y - __uint_as_float(r[j]));
+          r[j] = X3 ? tf32_rna(y) : __float_as_uint(y);       // (single TF32: operand truncation by the hardware, as in
+          lo[j] = __float_as_uint(y - __uint_as_float(r[j]));   //  any TF32 GEMM fed with float32 data)
         }
         tmem_st16(taddr + R0 + 16 * ch, r);
         if (X3) tmem_st16(taddr + R2 + 16 * ch, lo);
