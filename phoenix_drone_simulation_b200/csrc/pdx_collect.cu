@@ -43,7 +43,8 @@
 // tiles already cover.  Also slower: separate locks for the operand buffer X and the TMEM slot with one X buffer
 // per tile (X built while other tiles hold the slots, buffer released after layer 1, per-tile mbarriers): 1,470 vs
 // 1,400 us single TF32, 2,625 vs 2,295 us split TF32 -- every tile then queues for a slot at the same moment, where
-// the single lock staggers the tiles by itself.
+// the single lock staggers the tiles by itself.  Also slower (+1.2 %): skipping the actor's zero-weight hidden units in
+// the layer-3 dot products behind uniform branches.
 #define PDX_COL_LEADER_WAIT 0        // 1 = only the issuing warp waits at the hand-off barriers, the others arrive
 #endif
 #ifndef PDX_COL_NANOSLEEP
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
   // layer-2 biases ride on a constant-1 hidden unit after the actor's last one (the pack put a 1 into row D of B1
   // there, the actor's bias into that unit's row of B2a and the critic's into Bc): pi_h[0] < 64 is required
   const int EPC = B;                                           // environments per CTA and pass
+  const bool row_al8 = (D & 1) == 0;                           // rows start 8-byte aligned (tile base is 16-byte aligned)
 
   for (int64_t g = blockIdx.x; g < p.groups; g += gridDim.x) {
     const int64_t i = g * EPC + tid;
@@ -273,10 +275,20 @@ __global__ void __launch_bounds__(512, 1) k_collect(const __grid_constant__ KArg
       for (int kc = 0; kc < (D >> 2); ++kc) {                  // whole chunks
         uint32_t hi[4];
         float lo[4];
+        // (normaliser pairs as two 128-bit loads; the row as two 64-bit loads when its start is 8-byte aligned)
+        const float4 n01 = reinterpret_cast<const float4*>(norm)[2 * kc], n23 = reinterpret_cast<const float4*>(norm)[2 * kc + 1];
+        const float nmx[4] = {n01.x, n01.z, n23.x, n23.z}, nmy[4] = {n01.y, n01.w, n23.y, n23.w};
+        float o[4];
+        if (row_al8) {
+          const float2 a01 = reinterpret_cast<const float2*>(my_row)[2 * kc], a23 = reinterpret_cast<const float2*>(my_row)[2 * kc + 1];
+          o[0] = a01.x; o[1] = a01.y; o[2] = a23.x; o[3] = a23.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = my_row[4 * kc + j];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 nm = norm[4 * kc + j];
-          const float x = (my_row[4 * kc + j] - nm.x) * nm.y;
+          const float x = (o[j] - nmx[j]) * nmy[j];
           hi[j] = X3 ? tf32_rna(x) : __float_as_uint(x);      // single TF32: the tensor core drops the low 13 bits itself
           lo[j] = x - __uint_as_float(hi[j]);
         }
