@@ -44,7 +44,8 @@
 // per tile (X built while other tiles hold the slots, buffer released after layer 1, per-tile mbarriers): 1,470 vs
 // 1,400 us single TF32, 2,625 vs 2,295 us split TF32 -- every tile then queues for a slot at the same moment, where
 // the single lock staggers the tiles by itself.  Also slower (+1.2 %): skipping the actor's zero-weight hidden units in
-// the layer-3 dot products behind uniform branches.
+// the layer-3 dot products behind uniform branches.  No gain: the layer-3 dot products as packed FFMA2 (fma.rn.f32x2 with
+// a broadcast scalar: half the FMA instructions, same time).
 #define PDX_COL_LEADER_WAIT 0        // 1 = only the issuing warp waits at the hand-off barriers, the others arrive
 #endif
 #ifndef PDX_COL_NANOSLEEP
