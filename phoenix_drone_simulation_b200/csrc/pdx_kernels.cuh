@@ -610,6 +610,19 @@ __host__ __device__ inline size_t rollout_smem_bytes(int block, int D, int n_til
   return bytes + sizeof(double) * 4 * block;
 }
 
+// N consecutive float words of a thread's shared-memory row written as 64-bit stores: `dst` 8-byte aligned (ALIGNED)
+// or 4 bytes past an 8-byte boundary (one scalar store first).  fast2 rows are 2 E words long, so a row starts 8-byte
+// aligned and its second entry does when E is even.  Halves the store instructions of the row writes, and a
+// half warp's 64-bit accesses at the 34-word row stride are bank-conflict free (the 32-bit ones are 2-way).
+template <int N, bool ALIGNED>
+__device__ __forceinline__ void store_words64(float* dst, const float (&v)[N]) {
+  constexpr int first = ALIGNED ? 0 : 1;
+  if (!ALIGNED) dst[0] = v[0];
+#pragma unroll
+  for (int k = first; k + 1 < N; k += 2) *reinterpret_cast<float2*>(dst + k) = make_float2(v[k], v[k + 1]);
+  if ((N - first) & 1) dst[N - 1] = v[N - 1];
+}
+
 // per-thread context of the step loop: everything that is not the environment state itself
 template <class T>
 struct StepCtx {
@@ -832,16 +845,29 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
         __syncwarp();
       }
       if (valid) {
+        if constexpr (sizeof(T) == 4) {
+          if (fast2) {                                     // H == 2: entry 1 of this row, entry 0 of the next one
+            float ent[E];
 #pragma unroll
-        for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
+            for (int k = 0; k < C; ++k) ent[k] = (float)core[k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
-        if (fast2) {
-          T* nx = const_cast<T*>(to);
+            for (int k = 0; k < 4; ++k) ent[C + k] = (float)a_new[k];
+            store_words64<E, (E & 1) == 0>(reinterpret_cast<float*>(tn) + E, ent);
+            store_words64<E, true>(reinterpret_cast<float*>(const_cast<T*>(to)), ent);
+          }
+        }
+        if (!(sizeof(T) == 4 && fast2)) {
 #pragma unroll
-          for (int k = 0; k < C; ++k) nx[k] = core[k];
+          for (int k = 0; k < C; ++k) tn[(H - 1) * E + k] = core[k];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) nx[C + k] = a_new[k];
+          for (int k = 0; k < 4; ++k) tn[(H - 1) * E + C + k] = a_new[k];
+          if (fast2) {
+            T* nx = const_cast<T*>(to);
+#pragma unroll
+            for (int k = 0; k < C; ++k) nx[k] = core[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nx[C + k] = a_new[k];
+          }
         }
       }
     }
@@ -936,18 +962,36 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
           reset_env(m, rr, stale, o1, o2);
           w[L.ep_index] = (T)(16 * e_next);
         }
-        for (int j = 0; j < H; ++j) {                      // first observation of the new episode
+        bool rows_done = false;
+        if constexpr (sizeof(T) == 4) {
+          if (fast2) {                                     // H == 2: the whole row [o1 a | o2 a] and entry 0 of the next
+            float rw[2 * E];
 #pragma unroll
-          for (int k = 0; k < C; ++k) tn[j * E + k] = (j == H - 1) ? o2[k] : o1[k];
+            for (int k = 0; k < C; ++k) { rw[k] = (float)o1[k]; rw[E + k] = (float)o2[k]; }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
+            for (int k = 0; k < 4; ++k) { rw[C + k] = (float)w[L.last_action + k]; rw[E + C + k] = (float)w[L.last_action + k]; }
+            store_words64<2 * E, true>(reinterpret_cast<float*>(tn), rw);
+            float ent[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) ent[k] = rw[E + k];
+            store_words64<E, true>(reinterpret_cast<float*>(const_cast<T*>(to)), ent);
+            rows_done = true;
+          }
         }
-        if (fast2) {
-          T* nx = const_cast<T*>(to);
+        if (!rows_done) {
+          for (int j = 0; j < H; ++j) {                    // first observation of the new episode
 #pragma unroll
-          for (int k = 0; k < C; ++k) nx[k] = o2[k];
+            for (int k = 0; k < C; ++k) tn[j * E + k] = (j == H - 1) ? o2[k] : o1[k];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) nx[C + k] = w[L.last_action + k];
+            for (int k = 0; k < 4; ++k) tn[j * E + C + k] = w[L.last_action + k];
+          }
+          if (fast2) {
+            T* nx = const_cast<T*>(to);
+#pragma unroll
+            for (int k = 0; k < C; ++k) nx[k] = o2[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nx[C + k] = w[L.last_action + k];
+          }
         }
       }
     }
@@ -961,9 +1005,7 @@ __device__ __forceinline__ void rollout_step(const KArgs<T>& a, Model<T, TASK, P
       // used up since the last regeneration: a burst of very short episodes) -- so the take at the end of
       // a step never has to wait for a package.
       const int ew = (int)w[L.ep_index], e0 = ew >> 4, pend0 = ew & 15;
-      int total = 0;
-#pragma unroll
-      for (int sl = 0; sl < kPackSlots; ++sl) total += __popc(__ballot_sync(full, (pend0 >> sl) & 1));
+      const int total = (int)__reduce_add_sync(full, (unsigned)__popc(pend0));     // pending packages of the warp
       const bool urgent = (pend0 >> ((e0 + 1) & (kPackSlots - 1))) & 1;
 #if PDX_ACT_PREFETCH == 4
       // next step's action: requested here, so that its L2 latency runs under the vote barrier and the row copy
