@@ -55,6 +55,7 @@ int validate(const PdxConfig* c) {
 int check_buffers(const PdxConfig* c, const PdxBuffers* b, bool step) {
   if (!b) return fail(PDX_ERR_INVALID, "null buffers");
   if (b->n_envs <= 0) return fail(PDX_ERR_INVALID, "n_envs must be positive");
+  if (b->n_envs >= ((int64_t)1 << 31)) return fail(PDX_ERR_INVALID, "n_envs must be below 2^31 per shard");
   if (!b->state || !b->obs) return fail(PDX_ERR_INVALID, "state/obs buffers are required");
   if (step && (!b->reward || !b->cost || !b->terminated || !b->truncated))
     return fail(PDX_ERR_INVALID, "reward/cost/terminated/truncated buffers are required");

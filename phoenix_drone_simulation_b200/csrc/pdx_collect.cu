@@ -568,7 +568,7 @@ extern "C" int pdx_collect(const PdxConfig* cfg, const PdxBuffers* buf, const Pd
     return set_error(PDX_ERR_INVALID, "pdx_collect: n_steps must be in [1, 2^20] and obs0 / act / val / logp / last_val are required");
   if (!out->scratch || out->scratch_bytes < pdx_collect_scratch_bytes(buf->device))
     return set_error(PDX_ERR_INVALID, "pdx_collect: scratch buffer of pdx_collect_scratch_bytes() bytes required");
-  if (buf->n_envs <= 0 || !buf->state || !buf->obs || !buf->reward || !buf->cost || !buf->terminated || !buf->truncated)
+  if (buf->n_envs <= 0 || buf->n_envs >= ((int64_t)1 << 31) || !buf->state || !buf->obs || !buf->reward || !buf->cost || !buf->terminated || !buf->truncated)
     return set_error(PDX_ERR_INVALID, "pdx_collect: state / obs / reward / cost / terminated / truncated buffers are required");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(PDX_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path"); }

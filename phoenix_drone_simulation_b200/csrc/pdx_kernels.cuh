@@ -315,7 +315,8 @@ __device__ __forceinline__ int pool_plane(int history) {
 }
 template <class Mo, class T>
 __device__ __forceinline__ T* package_ptr(T* state, int64_t n, int64_t j, int history, int slot) {
-  return state + (((int64_t)pool_plane<Mo>(history) * n + ((int64_t)slot * n + j) * Mo::L.pack_quads) << 2);
+  const int n32 = (int)n;                                // n < 2^31 (checked at the ABI): 32 x 32 -> 64 bit products
+  return state + (((int64_t)pool_plane<Mo>(history) * n32 + ((int64_t)slot * n32 + j) * Mo::L.pack_quads) << 2);
 }
 template <class T> __device__ __forceinline__ void load_quad_at(const T* p, int q, T* out) { load_quad(p, (int64_t)0, (int64_t)q, 0, out); }
 template <class T> __device__ __forceinline__ void store_quad_at(T* p, int q, const T* in) { store_quad(p, (int64_t)0, (int64_t)q, 0, in); }

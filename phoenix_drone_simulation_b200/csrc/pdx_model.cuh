@@ -38,13 +38,17 @@ template <class T> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };   // two 128-bit accesses
 
+// quad index of (plane q, environment i): n < 2^31 (checked at the ABI), so the product is ONE 32 x 32 -> 64 bit
+// multiply-add instead of the three instructions of a 64-bit product
+__device__ __forceinline__ int64_t quad_index(int q, int64_t n, int64_t i) { return (int64_t)q * (int64_t)(int)n + i; }
+
 template <class T>
 __device__ __forceinline__ void load_quad(const T* base, int64_t n, int64_t i, int q, T* out) {
   if (sizeof(T) == 4) {
-    const float4 v = reinterpret_cast<const float4*>(base)[(int64_t)q * n + i];
+    const float4 v = reinterpret_cast<const float4*>(base)[quad_index(q, n, i)];
     out[0] = (T)v.x; out[1] = (T)v.y; out[2] = (T)v.z; out[3] = (T)v.w;
   } else {
-    const double2* p = reinterpret_cast<const double2*>(base) + ((int64_t)q * n + i) * 2;
+    const double2* p = reinterpret_cast<const double2*>(base) + quad_index(q, n, i) * 2;
     const double2 a = p[0], b = p[1];
     out[0] = (T)a.x; out[1] = (T)a.y; out[2] = (T)b.x; out[3] = (T)b.y;
   }
@@ -53,10 +57,10 @@ __device__ __forceinline__ void load_quad(const T* base, int64_t n, int64_t i, i
 template <class T>
 __device__ __forceinline__ void store_quad(T* base, int64_t n, int64_t i, int q, const T* in) {
   if (sizeof(T) == 4) {
-    reinterpret_cast<float4*>(base)[(int64_t)q * n + i] =
+    reinterpret_cast<float4*>(base)[quad_index(q, n, i)] =
         make_float4((float)in[0], (float)in[1], (float)in[2], (float)in[3]);
   } else {
-    double2* p = reinterpret_cast<double2*>(base) + ((int64_t)q * n + i) * 2;
+    double2* p = reinterpret_cast<double2*>(base) + quad_index(q, n, i) * 2;
     p[0] = make_double2((double)in[0], (double)in[1]);
     p[1] = make_double2((double)in[2], (double)in[3]);
   }

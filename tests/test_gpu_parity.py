@@ -163,7 +163,8 @@ def test_float32_production_kernel_matches_dump_and_oracle(env_id):
     obs0, rt = env.dump_reset()
     obs0 = obs0.double().cpu().numpy().copy()
     # (explicit reset: production k_reset vs the dump instantiation of k_reset -- same tolerance as the steps)
-    assert float((twin.reset() - env.obs).abs().max()) <= 2e-6 and torch.equal(fused.reset(), twin.obs)
+    o_twin = twin.reset()
+    assert float(((o_twin - env.obs).abs() / (1 + env.obs.abs())).max()) <= 4e-6 and torch.equal(fused.reset(), twin.obs)
     cols = list(range(0, N, 173))                      # oracle replays these environments
     reset_tapes = {c: [rt[:, c].cpu().numpy().copy()] for c in cols}
     step_tapes = {c: [] for c in cols}
