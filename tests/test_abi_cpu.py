@@ -157,6 +157,9 @@ def test_empty_batch_is_rejected_before_any_cuda_call(lib):
     assert lib.pdx_step(C.byref(c), C.byref(b), None, 0, 0, None) == -1
     assert b'n_envs' in lib.pdx_last_error()
     assert lib.pdx_step_many(C.byref(c), C.byref(b), None, 0, 0, 0, None) == -1
+    b.n_envs = 1 << 31                                   # the maximum shard: index products are 32 x 32 -> 64 bit
+    assert lib.pdx_step(C.byref(c), C.byref(b), None, 0, 0, None) == -1
+    assert b'2^31' in lib.pdx_last_error()
 
 
 def test_tensor_core_policy_shape_checks_need_no_device(lib):
