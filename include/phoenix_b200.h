@@ -121,7 +121,7 @@ typedef struct PdxConfig {
 #define PDX_BUF_STATE_STABLE 1
 
 typedef struct PdxBuffers {
-  int64_t n_envs;               /* environments in this shard                             */
+  int64_t n_envs;               /* environments in this shard, 1 .. 2^31 - 1              */
   int64_t env_offset;           /* global index of local env 0 (RNG subsequence)          */
   int32_t device;               /* CUDA device ordinal the buffers live on                */
   int32_t flags;                /* PDX_BUF_* bits, 0 = none                               */
