@@ -39,6 +39,9 @@ template <> struct M<float> {
   static __device__ __forceinline__ float unit(uint32_t a) {             // [0,1)
     return __uint_as_float(0x3f800000u | (a >> 9)) - 1.0f;
   }
+  static __device__ __forceinline__ float unit21(uint32_t u) {           // [0,1) from a 21-bit integer
+    return __uint_as_float(0x3f800000u | (u << 2)) - 1.0f;
+  }
 };
 
 template <> struct M<double> {
@@ -62,6 +65,9 @@ template <> struct M<double> {
   }
   static __device__ __forceinline__ double unit(uint32_t a) {            // [0,1)
     return (double)a * (1.0 / 4294967296.0);
+  }
+  static __device__ __forceinline__ double unit21(uint32_t u) {          // [0,1) from a 21-bit integer
+    return (double)u * (1.0 / 2097152.0);
   }
 };
 
@@ -130,7 +136,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // of K variates occupies ceil(K/4) consecutive ids.
 enum DrawSite : uint32_t {
   SITE_SUBSTEP = 0,      // + 8*substep : +0..2  OU(4n) + gyro bias (3n) + gyro white noise (3n)
-  SITE_FINAL_OBS = 64,   // +0..3 normals: pos(3) vel(3) gyro bias(3) gyro white(3) theta(3); +4,+5 uniforms: pos(3) theta(3)
+  SITE_FINAL_OBS = 64,   // +0..3 normals: pos(3) vel(3) gyro bias(3) gyro white(3) theta(3); +4 uniforms: pos(3) theta(3) (21 bits each)
   SITE_RESET = 80,       // +0..3 task uniforms (<=14), +4..6 motor x / ring rows normals (4+8)
   SITE_DR = 88,          // +0..3 dt,m,Jx,Jy,Jz,ftf0,ftf1, motor T(4), T2W(4) uniforms
   SITE_RESET_OBS1 = 96,  // like SITE_FINAL_OBS
@@ -182,6 +188,18 @@ struct Rng {
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (4 * c + k < K) out[4 * c + k] = M<T>::unit(v[k]);
     }
+  }
+  // Six unit uniforms from ONE call: 21 bits each (the high 21 bits of the four words, and the low 11 + 10 bits of
+  // two word pairs).  The float32 path keeps 23 bits of a word anyway; the sensor model's uniform terms are +-1 mm and
+  // +-0.05 degrees wide.  Saves one of the six Philox calls of an observation.
+  __device__ __forceinline__ void gen_uniforms6(uint32_t site, T* out) const {
+    const uint4 r = raw(site);
+    out[0] = M<T>::unit21(r.x >> 11);
+    out[1] = M<T>::unit21(r.y >> 11);
+    out[2] = M<T>::unit21(r.z >> 11);
+    out[3] = M<T>::unit21(r.w >> 11);
+    out[4] = M<T>::unit21(((r.x & 0x7FFu) << 10) | (r.y & 0x3FFu));
+    out[5] = M<T>::unit21(((r.z & 0x7FFu) << 10) | (r.w & 0x3FFu));
   }
   // Raw generation (no tape, no dump): what the production path consumes.
   template <int K> __device__ __forceinline__ void gen_normals(uint32_t site0, T* out) const { philox_normals<K>(site0, out); }

@@ -459,7 +459,7 @@ struct Model {
       } else {
         T zn[15];
         rng.template gen_normals<15>(site0, zn);
-        rng.template gen_uniforms<6>(site0 + 4, zu);
+        rng.gen_uniforms6(site0 + 4, zu);
         gyro_update_merged(&zn[6], &zn[9], om);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
