@@ -400,6 +400,16 @@ def test_normal_draws_are_standard():
                    white(ts[52:55], ts[55:58]), ts[58:61]]).flatten()
     u = torch.cat([ts[40:43], ts[61:64]]).flatten()                                           # uniform slots
     assert 0 <= float(u.min()) and float(u.max()) < 1 and abs(float(u.mean()) - 0.5) < 3e-3
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.06                                           # kurtosis of a normal
+    # the six uniforms of an observation share ONE Philox call (21 bits each: the high 21 bits of the four words and
+    # the low 11 + 10 bits of two word pairs): right variance, 21-bit grid, no correlation between the six
+    assert abs(float(u.var()) - 1.0 / 12.0) < 1e-3
+    g = u.double() * 2 ** 21
+    assert torch.equal(g, g.round())
+    six = torch.cat([ts[40:43], ts[61:64]]).double()                                          # [6][N]
+    c = torch.corrcoef(six)
+    assert float((c - torch.eye(6, device=c.device, dtype=c.dtype)).abs().max()) < 0.02
 
 
 def test_single_env_dropin_api():
